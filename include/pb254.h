@@ -1,0 +1,94 @@
+/* pb254.h — C ABI of the B200-native starky prover for plonky2_bn254's BN254 STARKs.
+ *
+ * Drop-in boundary: the entry points below are what an FFI crate binds in place of
+ * the bodies of
+ *   G1ScalarMulStark::generate_trace   src/starks/curves/g1/scalar_mul_stark.rs:55-69
+ *   G2ScalarMulStark::generate_trace   src/starks/curves/g2/scalar_mul_stark.rs:55-69
+ *   FqExpStark::generate_trace         src/starks/fields/exp_stark.rs:53-67
+ *   prove()                            src/starks/common/prover.rs:18-72
+ *   verify()                           src/starks/common/verifier.rs:32-98
+ * as called from G1/G2/FqStarkProofGenerator::run_once
+ *   (src/generators/g1/stark_proof.rs:136-179, g2/stark_proof.rs:136, fq/stark_proof.rs:135).
+ *
+ * Plain pointers and sizes only. All field elements are canonical little-endian u64 (< p).
+ * Input wire format, one row per instance, each 256-bit value as 4 little-endian u64 words:
+ *   kind G1: s, x.x, x.y, offset.x, offset.y                                   (20 words)
+ *   kind G2: s, x.x.c0, x.x.c1, x.y.c0, x.y.c1, offset.x.c0, ... offset.y.c1   (36 words)
+ *   kind FQ: s, x                                                              (8 words)
+ * `s` is any value < 2^256 (not reduced); coordinates must be canonical (< p) affine, non-infinity.
+ * `timestamps[i]` is the CTL timestamp of instance i (the reference uses the batch index).
+ */
+#ifndef PB254_H
+#define PB254_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PB254_KIND_G1 = 0, PB254_KIND_G2 = 1, PB254_KIND_FQ = 2 };
+
+/* return codes (the reference panics / returns anyhow::Error at these points) */
+enum {
+  PB254_OK = 0,
+  PB254_E_SCALAR_RANGE = 1,  /* common/utils.rs:4   scalar wider than 256 bits (unreachable on this wire format) */
+  PB254_E_INFINITY = 2,      /* g1/add.rs:49-51     an intermediate a = -b (point at infinity) */
+  PB254_E_NOT_CANONICAL = 3, /* coordinate >= p */
+  PB254_E_CUDA = 4,          /* CUDA runtime failure */
+  PB254_E_OOM = 5,           /* device allocation failure */
+  PB254_E_BAD_ARG = 6,
+  PB254_E_VERIFY = 7         /* verifier.rs: proof rejected */
+};
+
+/* StarkConfig (starky config.rs; the reference hard-wires standard_fast_config() at
+ * src/generators/g1/stark_proof.rs:85,152) */
+typedef struct pb254_config {
+  uint32_t rate_bits;        /* 1 */
+  uint32_t cap_height;       /* 4 */
+  uint32_t num_challenges;   /* 2 */
+  uint32_t num_query_rounds; /* 84 */
+  uint32_t pow_bits;         /* 16 */
+  uint32_t arity_bits;       /* 4  (FriReductionStrategy::ConstantArityBits(4, 5)) */
+  uint32_t final_poly_bits;  /* 5 */
+} pb254_config;
+
+typedef struct pb254_ctx pb254_ctx;
+typedef struct pb254_proof pb254_proof;
+
+void pb254_config_standard_fast(pb254_config* out);
+
+/* One context per GPU; a context may be used by one thread at a time. `stream` is a cudaStream_t
+ * (0 / NULL = the library creates its own stream). */
+int pb254_ctx_create(int device, void* stream, pb254_ctx** out);
+void pb254_ctx_destroy(pb254_ctx* ctx);
+const char* pb254_last_error(void);
+/* number of CUDA kernels this library has launched in this process */
+uint64_t pb254_launch_count(void);
+
+/* device time (CUDA events on the context's stream) of the stages of the last call, in ms */
+int pb254_timing_count(pb254_ctx* ctx);
+const char* pb254_timing_name(pb254_ctx* ctx, int i);
+double pb254_timing_ms(pb254_ctx* ctx, int i);
+
+/* shapes */
+int pb254_trace_width(int kind);                  /* 781 / 1295 / 427 */
+int pb254_input_words(int kind);                  /* 20 / 36 / 8 */
+int pb254_num_aux(int kind, uint32_t num_challenges); /* 456 / 906 / 134 for 2 challenges */
+size_t pb254_trace_rows(size_t n_inputs, size_t min_rows);
+
+/* ---- building blocks (exposed for parity tests and reuse) ----------------------------------- */
+/* Poseidon permutation of n states (12 words each), on the device. */
+int pb254_poseidon_permute(pb254_ctx* ctx, const uint64_t* states_in, size_t n, uint64_t* states_out);
+/* K3: LDE of a host column-major matrix (cols x n) -> host (cols x n<<rate_bits), natural order. */
+int pb254_lde_batch(pb254_ctx* ctx, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits,
+                    int from_coeffs, uint64_t* lde_out);
+/* K3+K4+K5: PolynomialBatch::from_values / from_coeffs of a host column-major matrix: Merkle cap
+ * (2^cap_height x 4 words) and, optionally, all digest levels bottom-up. */
+int pb254_commit(pb254_ctx* ctx, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits,
+                 uint32_t cap_height, int from_coeffs, uint64_t* cap_out, uint64_t* digests_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PB254_H */

@@ -1,0 +1,116 @@
+// K4 `leaf_hash` + K5 `merkle_levels`: Poseidon Merkle tree with cap over a column-major LDE.
+// Replaces MerkleTree::new of plonky2 0.2.2 hash/merkle_tree.rs as used by PolynomialBatch
+// (un-vendored; call site src/starks/common/prover.rs:31-38):
+//   leaf i = LDE row rev(i);  digest = hash_or_noop(row) (rows of <= 4 elements are NOT hashed);
+//   parent = two_to_one(left, right);  cap = level with 2^cap_height nodes.
+// Layout: the LDE stays column-major [col][N] in natural row order; thread j reads element j of
+// every column (a warp reads 256 contiguous bytes per column, fully coalesced, no transpose) and
+// writes its 32-byte digest at the bit-reversed position. Digest levels are stored bottom-up in
+// one array: level 0 (N digests) | level 1 (N/2) | ... | cap.
+// Algorithmic bytes: 8 W N (read) + 32 (2N - 2^cap_height) (digests); the leaf kernel is bound by
+// the integer pipe (ceil(W/8) permutations per row), not by HBM.
+#pragma once
+#include "poseidon.cuh"
+
+namespace merkle {
+
+using poseidon::Digest;
+
+struct LeafHashK {
+  const u64* lde;
+  size_t stride;
+  int W, log_n;
+  Digest* out;
+  PB_HD void operator()(size_t j) const {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    if (W <= 4) {  // hash_or_noop
+      for (int c = 0; c < W; c++) s[c] = lde[(size_t)c * stride + j];
+    } else {
+      int c = 0;
+      for (; c + 8 <= W; c += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = lde[(size_t)(c + k) * stride + j];
+        poseidon::permute(s);
+      }
+      if (c < W) {
+        for (int k = 0; c + k < W; k++) s[k] = lde[(size_t)(c + k) * stride + j];
+        poseidon::permute(s);
+      }
+    }
+    Digest d;
+#pragma unroll
+    for (int i = 0; i < 4; i++) d.e[i] = s[i];
+    out[gl::brev32((u32)j, log_n)] = d;
+  }
+};
+
+// leaves stored row-major and already in leaf order (FRI layers): leaf i = rows[i*len .. +len)
+struct RowHashK {
+  const u64* rows;
+  int len;
+  Digest* out;
+  PB_HD void operator()(size_t i) const {
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+    const u64* row = rows + i * (size_t)len;
+    if (len <= 4) {
+      for (int c = 0; c < len; c++) s[c] = row[c];
+    } else {
+      for (int c = 0; c < len; c += 8) {
+        for (int k = 0; k < 8 && c + k < len; k++) s[k] = row[c + k];
+        poseidon::permute(s);
+      }
+    }
+    Digest d;
+#pragma unroll
+    for (int k = 0; k < 4; k++) d.e[k] = s[k];
+    out[i] = d;
+  }
+};
+
+struct LevelK {
+  const Digest* child;
+  Digest* parent;
+  PB_HD void operator()(size_t i) const { parent[i] = poseidon::two_to_one(child[2 * i], child[2 * i + 1]); }
+};
+
+static inline size_t tree_digests(int log_n, int cap_height) {
+  size_t total = 0;
+  for (int l = log_n; l >= cap_height; l--) total += (size_t)1 << l;
+  return total;
+}
+// offset (in digests) of level `lvl` (0 = leaves)
+static inline size_t level_offset(int log_n, int lvl) {
+  size_t off = 0;
+  for (int l = 0; l < lvl; l++) off += (size_t)1 << (log_n - l);
+  return off;
+}
+
+static inline void build_levels(Digest* digests, int log_n, int cap_height, pbStream s) {
+  if (cap_height > log_n) throw Pb254Error(6, "merkle: cap_height > log2(leaves)");
+  size_t off = 0;
+  for (int l = 0; l < log_n - cap_height; l++) {
+    size_t m = (size_t)1 << (log_n - l);
+    LevelK k{digests + off, digests + off + m};
+    pb_launch("merkle level", k, m / 2, s, 128);
+    off += m;
+  }
+}
+
+// digests: tree_digests(log_n, cap_height) entries; the cap is the last 2^cap_height of them
+static inline void build_from_lde(const u64* lde, size_t stride, int W, int log_n, int cap_height, Digest* digests,
+                                  pbStream s) {
+  LeafHashK k{lde, stride, W, log_n, digests};
+  pb_launch("leaf hash", k, (size_t)1 << log_n, s, 128);
+  build_levels(digests, log_n, cap_height, s);
+}
+static inline void build_from_rows(const u64* rows, int len, int log_n, int cap_height, Digest* digests, pbStream s) {
+  RowHashK k{rows, len, digests};
+  pb_launch("row hash", k, (size_t)1 << log_n, s, 128);
+  build_levels(digests, log_n, cap_height, s);
+}
+
+}  // namespace merkle

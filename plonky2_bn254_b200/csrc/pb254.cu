@@ -1,0 +1,193 @@
+// Unity translation unit of libpb254.so: kernels + host orchestration + C ABI (include/pb254.h).
+// Built by plonky2_bn254_b200/build.py with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// (or, test-only, g++ -x c++ -DPB254_HOSTSIM for the host-simulation library under tests/hostsim/).
+#include "../../include/pb254.h"
+#include "compat.cuh"
+#if !PB_HOSTSIM
+unsigned long long g_pb_launches = 0;
+#else
+static unsigned long long g_pb_launches = 0;
+#endif
+#include "context.cuh"
+#include "merkle.cuh"
+
+namespace {
+thread_local std::string g_last_error;
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return PB254_OK;
+  } catch (const Pb254Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return PB254_E_BAD_ARG;
+  }
+}
+
+int ilog2_strict(size_t n) {
+  int k = 0;
+  while (((size_t)1 << k) < n) k++;
+  if (((size_t)1 << k) != n) throw Pb254Error(PB254_E_BAD_ARG, "size is not a power of two");
+  return k;
+}
+
+struct Shape {
+  int L, width, aux_len, in_words;
+};
+Shape shape_for(int kind) {
+  switch (kind) {
+    case PB254_KIND_G1: return {32, 781, 354, 20};
+    case PB254_KIND_G2: return {64, 1295, 708, 36};
+    case PB254_KIND_FQ: return {16, 427, 80, 8};
+  }
+  throw Pb254Error(PB254_E_BAD_ARG, "unknown STARK kind");
+}
+
+struct PermuteK {
+  const u64* in;
+  u64* out;
+  PB_HD void operator()(size_t i) const {
+    u64 s[12];
+    for (int k = 0; k < 12; k++) s[k] = in[i * 12 + k];
+    poseidon::permute(s);
+    for (int k = 0; k < 12; k++) out[i * 12 + k] = s[k];
+  }
+};
+}  // namespace
+
+extern "C" {
+
+void pb254_config_standard_fast(pb254_config* c) {
+  c->rate_bits = 1;
+  c->cap_height = 4;
+  c->num_challenges = 2;
+  c->num_query_rounds = 84;
+  c->pow_bits = 16;
+  c->arity_bits = 4;
+  c->final_poly_bits = 5;
+}
+
+const char* pb254_last_error(void) { return g_last_error.c_str(); }
+uint64_t pb254_launch_count(void) { return g_pb_launches; }
+
+int pb254_ctx_create(int device, void* stream, pb254_ctx** out) {
+  return guarded([&] {
+    if (!out) throw Pb254Error(PB254_E_BAD_ARG, "null out pointer");
+    pb_set_device(device);
+    pb254_ctx* c = new pb254_ctx();
+    c->device = device;
+#if PB_HOSTSIM
+    c->stream = stream;
+#else
+    if (stream) {
+      c->stream = (cudaStream_t)stream;
+    } else {
+      PB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      c->own_stream = true;
+    }
+#endif
+    c->tables.init(c->stream);
+    *out = c;
+  });
+}
+
+void pb254_ctx_destroy(pb254_ctx* c) {
+  if (!c) return;
+  c->times.clear();
+  c->tables.destroy();
+  c->arena.destroy();
+#if !PB_HOSTSIM
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+#endif
+  delete c;
+}
+
+/* stage timings of the last call on this context (device time, ms) */
+int pb254_timing_count(pb254_ctx* c) { return (int)c->times.recs.size(); }
+const char* pb254_timing_name(pb254_ctx* c, int i) { return c->times.recs[i].name.c_str(); }
+double pb254_timing_ms(pb254_ctx* c, int i) { return c->times.recs[i].ms; }
+
+int pb254_trace_width(int kind) { return kind >= 0 && kind <= 2 ? shape_for(kind).width : -1; }
+int pb254_input_words(int kind) { return kind >= 0 && kind <= 2 ? shape_for(kind).in_words : -1; }
+int pb254_num_aux(int kind, uint32_t nch) {
+  if (kind < 0 || kind > 2) return -1;
+  Shape s = shape_for(kind);
+  int ncols = 3 * s.L + s.aux_len;
+  return ((ncols + 1) / 2 + 1 + 2) * (int)nch;
+}
+size_t pb254_trace_rows(size_t n_inputs, size_t min_rows) {
+  size_t n = n_inputs * 512 > min_rows ? n_inputs * 512 : min_rows, r = 1;
+  while (r < n) r <<= 1;
+  return r;
+}
+
+int pb254_poseidon_permute(pb254_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
+  return guarded([&] {
+    pb_set_device(c->device);
+    c->arena.reserve(2 * n * 96 + 1024);
+    c->arena.reset();
+    u64* din = c->arena.alloc_n<u64>(n * 12);
+    u64* dout = c->arena.alloc_n<u64>(n * 12);
+    pb_h2d(din, in, n * 96, c->stream);
+    pb_launch("poseidon permute", PermuteK{din, dout}, n, c->stream, 128);
+    pb_d2h(out, dout, n * 96, c->stream);
+    pb_sync(c->stream);
+  });
+}
+
+int pb254_lde_batch(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits, int from_coeffs,
+                    uint64_t* lde_out) {
+  return guarded([&] {
+    pb_set_device(c->device);
+    int L = ilog2_strict(n);
+    size_t N = n << rate_bits;
+    c->arena.reserve((2 * cols * n + cols * N) * 8 + 4096);
+    c->arena.reset();
+    u64* dv = c->arena.alloc_n<u64>(cols * n);
+    u64* scratch = c->arena.alloc_n<u64>(cols * n);
+    u64* lde = c->arena.alloc_n<u64>(cols * N);
+    pb_h2d(dv, values, cols * n * 8, c->stream);
+    ntt::lde_columns(c->tables, dv, n, lde, N, scratch, (int)cols, L, (int)rate_bits,
+                     from_coeffs ? ntt::FROM_COEFFS_LDE : ntt::FROM_VALUES_LDE, c->stream);
+    pb_d2h(lde_out, lde, cols * N * 8, c->stream);
+    pb_sync(c->stream);
+  });
+}
+
+int pb254_commit(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits, uint32_t cap_height,
+                 int from_coeffs, uint64_t* cap_out, uint64_t* digests_out) {
+  return guarded([&] {
+    pb_set_device(c->device);
+    int L = ilog2_strict(n);
+    size_t N = n << rate_bits;
+    int log_N = L + (int)rate_bits;
+    size_t nd = merkle::tree_digests(log_N, (int)cap_height);
+    c->arena.reserve((2 * cols * n + cols * N) * 8 + nd * 32 + 4096);
+    c->arena.reset();
+    u64* dv = c->arena.alloc_n<u64>(cols * n);
+    u64* scratch = c->arena.alloc_n<u64>(cols * n);
+    u64* lde = c->arena.alloc_n<u64>(cols * N);
+    merkle::Digest* dig = c->arena.alloc_n<merkle::Digest>(nd);
+    pb_h2d(dv, values, cols * n * 8, c->stream);
+    c->times.clear();
+    int t0 = c->times.begin("lde", c->stream);
+    ntt::lde_columns(c->tables, dv, n, lde, N, scratch, (int)cols, L, (int)rate_bits,
+                     from_coeffs ? ntt::FROM_COEFFS_LDE : ntt::FROM_VALUES_LDE, c->stream);
+    c->times.end(t0, c->stream);
+    int t1 = c->times.begin("merkle", c->stream);
+    merkle::build_from_lde(lde, N, (int)cols, log_N, (int)cap_height, dig, c->stream);
+    c->times.end(t1, c->stream);
+    size_t ncap = (size_t)1 << cap_height;
+    pb_d2h(cap_out, dig + (nd - ncap), ncap * 32, c->stream);
+    if (digests_out) pb_d2h(digests_out, dig, nd * 32, c->stream);
+    pb_sync(c->stream);
+    c->times.resolve();
+  });
+}
+
+}  // extern "C"

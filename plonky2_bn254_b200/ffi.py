@@ -1,0 +1,165 @@
+"""ctypes binding of the C ABI in include/pb254.h (libpb254.so, CUDA sm_100a).
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is present, loading / context
+creation raises. (Tests for host-side logic may bind the test-only host-simulation build by passing
+an explicit path to :class:`Library`; the product never does.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpb254.so")
+
+KIND_G1, KIND_G2, KIND_FQ = 0, 1, 2
+
+ERROR_NAMES = {
+    0: "OK", 1: "E_SCALAR_RANGE", 2: "E_INFINITY", 3: "E_NOT_CANONICAL", 4: "E_CUDA", 5: "E_OOM", 6: "E_BAD_ARG",
+    7: "E_VERIFY",
+}
+
+
+class Pb254Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pb254 error {code} ({ERROR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("rate_bits", "cap_height", "num_challenges", "num_query_rounds", "pow_bits", "arity_bits",
+                 "final_poly_bits")]
+
+    def as_tuple(self):
+        return tuple(getattr(self, n) for n, _ in self._fields_)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Library:
+    """A loaded libpb254 (product) or, for host-logic tests only, the hostsim build."""
+
+    def __init__(self, path: str | None = None):
+        path = path or LIB_PATH
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build it with `python -m plonky2_bn254_b200.build` "
+                "(there is no CPU fallback for the prover)")
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.pb254_last_error.restype = C.c_char_p
+        L.pb254_launch_count.restype = C.c_uint64
+        L.pb254_trace_rows.restype = C.c_size_t
+        L.pb254_trace_rows.argtypes = [C.c_size_t, C.c_size_t]
+        L.pb254_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.pb254_ctx_destroy.argtypes = [C.c_void_p]
+        L.pb254_timing_count.argtypes = [C.c_void_p]
+        L.pb254_timing_name.argtypes = [C.c_void_p, C.c_int]
+        L.pb254_timing_name.restype = C.c_char_p
+        L.pb254_timing_ms.argtypes = [C.c_void_p, C.c_int]
+        L.pb254_timing_ms.restype = C.c_double
+        for name in ("pb254_proof_words",):
+            if hasattr(L, name):
+                getattr(L, name).restype = C.c_size_t
+
+    def check(self, rc):
+        if rc != 0:
+            raise Pb254Error(rc, self.lib.pb254_last_error().decode())
+
+    def standard_fast_config(self) -> Config:
+        c = Config()
+        self.lib.pb254_config_standard_fast(C.byref(c))
+        return c
+
+    def launch_count(self) -> int:
+        return int(self.lib.pb254_launch_count())
+
+    def trace_width(self, kind):
+        return self.lib.pb254_trace_width(kind)
+
+    def input_words(self, kind):
+        return self.lib.pb254_input_words(kind)
+
+    def num_aux(self, kind, num_challenges=2):
+        return self.lib.pb254_num_aux(kind, num_challenges)
+
+    def trace_rows(self, n_inputs, min_rows):
+        return self.lib.pb254_trace_rows(n_inputs, min_rows)
+
+
+_default = None
+
+
+def default_library() -> Library:
+    global _default
+    if _default is None:
+        _default = Library()
+    return _default
+
+
+class Context:
+    """One prover context per GPU (pb254_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None, library: Library | None = None):
+        self.L = library or default_library()
+        h = C.c_void_p()
+        self.L.check(self.L.lib.pb254_ctx_create(device, C.c_void_p(stream or 0), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.lib.pb254_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def timings(self):
+        """[(stage name, device ms)] of the last call on this context."""
+        n = self.L.lib.pb254_timing_count(self._h)
+        return [(self.L.lib.pb254_timing_name(self._h, i).decode(), self.L.lib.pb254_timing_ms(self._h, i))
+                for i in range(n)]
+
+    # ---- building blocks ------------------------------------------------------------------
+    def poseidon_permute(self, states):
+        s = _u64(states).reshape(-1, 12)
+        out = np.empty_like(s)
+        self.L.check(self.L.lib.pb254_poseidon_permute(self._h, _p(s), C.c_size_t(s.shape[0]), _p(out)))
+        return out
+
+    def lde_batch(self, values, rate_bits, from_coeffs=False):
+        v = _u64(values)
+        cols, n = v.shape
+        out = np.empty((cols, n << rate_bits), dtype=np.uint64)
+        self.L.check(self.L.lib.pb254_lde_batch(self._h, _p(v), C.c_size_t(cols), C.c_size_t(n), C.c_uint32(rate_bits),
+                                                C.c_int(int(from_coeffs)), _p(out)))
+        return out
+
+    def commit(self, values, rate_bits, cap_height, from_coeffs=False, want_digests=False):
+        v = _u64(values)
+        cols, n = v.shape
+        cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+        dig = None
+        if want_digests:
+            N = n << rate_bits
+            total, m = 0, N
+            while m >= (1 << cap_height):
+                total += m
+                m //= 2
+            dig = np.empty((total, 4), dtype=np.uint64)
+        self.L.check(self.L.lib.pb254_commit(self._h, _p(v), C.c_size_t(cols), C.c_size_t(n), C.c_uint32(rate_bits),
+                                             C.c_uint32(cap_height), C.c_int(int(from_coeffs)), _p(cap), _p(dig)))
+        return (cap, dig) if want_digests else cap
