@@ -88,6 +88,13 @@ int pb254_lde_batch(pb254_ctx* ctx, const uint64_t* values, size_t cols, size_t 
 int pb254_commit(pb254_ctx* ctx, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits,
                  uint32_t cap_height, int from_coeffs, uint64_t* cap_out, uint64_t* digests_out);
 
+/* ---- trace generation (K1 + K2) -------------------------------------------------------------- */
+/* generate_trace(&inputs, min_rows): fills cols_out, column-major pb254_trace_width(kind) x
+ * pb254_trace_rows(n_inputs, min_rows), with the bit-exact trace of the reference. min_rows must make
+ * the trace at least 2^16 rows (the reference passes 1 << 16). */
+int pb254_generate_trace(pb254_ctx* ctx, int kind, const uint64_t* inputs, const uint64_t* timestamps,
+                         size_t n_inputs, size_t min_rows, uint64_t* cols_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,8 +26,8 @@ struct Pb254Error : std::runtime_error {
 
 #ifdef PB254_HOSTSIM
 // ------------------------------------------------------------------------------------------
-#define PB_HD
-#define PB_D
+#define PB_HD inline
+#define PB_D inline
 #define PB_INLINE inline
 #define PB_HOSTSIM 1
 typedef void* pbStream;
@@ -45,6 +45,7 @@ static inline void pb_memset(void* d, int v, size_t n, pbStream) { memset(d, v, 
 static inline void pb_sync(pbStream) {}
 static inline void pb_set_device(int) {}
 
+extern unsigned long long g_pb_launches;
 template <class F>
 static inline void pb_launch(const char*, F f, size_t n, pbStream, int = 256) {
 #pragma omp parallel for schedule(static)

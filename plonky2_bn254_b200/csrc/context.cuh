@@ -1,7 +1,7 @@
 // Per-GPU prover context: stream, twiddle/shift tables and a bump-allocated device workspace that
 // is grown on demand and reused across proofs of the same shape (no cudaMalloc on the hot path).
 #pragma once
-#include "ntt.cuh"
+#include "ntt_tables.cuh"
 #include <vector>
 #include <string>
 #include <time.h>

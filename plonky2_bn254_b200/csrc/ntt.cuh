@@ -14,66 +14,9 @@
 // written out (openings and the FRI combination are computed from evaluations instead).
 // Algorithmic bytes per column: 8 n (2 + 2^r)  (SURVEY.md 8d); bound: HBM.
 #pragma once
-#include "gl.cuh"
-#include <vector>
+#include "ntt_tables.cuh"
 
 namespace ntt {
-
-static constexpr int LOG_T = 13;          // two-level power tables: x^e = lo[e & 8191] * hi[e >> 13]
-static constexpr int T = 1 << LOG_T;
-static constexpr int LOG_M = 2 * LOG_T;   // master root has order 2^26
-static constexpr int TC = 8;              // adjacent columns per strided tile (64-byte segments)
-static constexpr int KC_MAX = 10;
-static constexpr int K1_MAX = 11;
-
-struct Tables {
-  const u64 *fwd_lo, *fwd_hi;  // W^e,   W = root of unity of order 2^26
-  const u64 *inv_lo, *inv_hi;  // W^-e
-  const u64 *sh_lo, *sh_hi;    // 7^e
-  const u64 *ish_lo, *ish_hi;  // 7^-e
-};
-
-PB_HD u64 tpow(const u64* lo, const u64* hi, u64 e) { return gl::mul(lo[e & (T - 1)], hi[e >> LOG_T]); }
-
-static inline void host_build_table(u64 base, std::vector<u64>& lo, std::vector<u64>& hi) {
-  lo.resize(T);
-  hi.resize(T);
-  lo[0] = 1;
-  for (int i = 1; i < T; i++) lo[i] = gl::mul(lo[i - 1], base);
-  u64 step = gl::mul(lo[T - 1], base);
-  hi[0] = 1;
-  for (int i = 1; i < T; i++) hi[i] = gl::mul(hi[i - 1], step);
-}
-
-struct TableSet {
-  u64* dev = nullptr;  // 8 * T words
-  Tables t;
-  void init(pbStream s) {
-    std::vector<u64> all(8 * T), lo, hi;
-    u64 W = gl::root_of_unity(LOG_M);
-    u64 bases[4] = {W, gl::inv(W), gl::COSET_SHIFT, gl::inv(gl::COSET_SHIFT)};
-    for (int k = 0; k < 4; k++) {
-      host_build_table(bases[k], lo, hi);
-      memcpy(&all[(2 * k) * T], lo.data(), T * 8);
-      memcpy(&all[(2 * k + 1) * T], hi.data(), T * 8);
-    }
-    dev = (u64*)pb_dev_alloc(8 * T * 8);
-    pb_h2d(dev, all.data(), 8 * T * 8, s);
-    pb_sync(s);
-    t.fwd_lo = dev;
-    t.fwd_hi = dev + T;
-    t.inv_lo = dev + 2 * T;
-    t.inv_hi = dev + 3 * T;
-    t.sh_lo = dev + 4 * T;
-    t.sh_hi = dev + 5 * T;
-    t.ish_lo = dev + 6 * T;
-    t.ish_hi = dev + 7 * T;
-  }
-  void destroy() {
-    if (dev) pb_dev_free(dev);
-    dev = nullptr;
-  }
-};
 
 enum Mode { FROM_VALUES_LDE = 0, FROM_COEFFS_LDE = 1, INTT_COSET_NAT = 2 };
 
@@ -94,7 +37,7 @@ static inline Plan make_plan(int L, int r) {
 #if !PB_HOSTSIM
 // ---------------------------------------------------------------------------------------------
 // pass A: inverse DIF over the top K1 index bits; rows r = 0..2^K1-1 at stride C = 2^(L-K1).
-__global__ void __launch_bounds__(256) k_ntt_pass_a(const u64* __restrict__ in, u64* __restrict__ out, int L, int K1,
+static __global__ void __launch_bounds__(256) k_ntt_pass_a(const u64* __restrict__ in, u64* __restrict__ out, int L, int K1,
                                                     size_t in_stride, size_t out_stride, Tables t) {
   extern __shared__ u64 sm[];
   const int R = 1 << K1;
@@ -131,7 +74,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass_a(const u64* __restrict__ in, 
 }
 
 // fused contiguous kernel, one 2^Kc block of one column per CTA
-__global__ void __launch_bounds__(256) k_ntt_fused(const u64* __restrict__ in, u64* __restrict__ out, int L, int Kc,
+static __global__ void __launch_bounds__(256) k_ntt_fused(const u64* __restrict__ in, u64* __restrict__ out, int L, int Kc,
                                                    int r, size_t in_stride, size_t out_stride, Tables t, u64 ninv,
                                                    int mode) {
   extern __shared__ u64 sm[];
@@ -208,7 +151,7 @@ __global__ void __launch_bounds__(256) k_ntt_fused(const u64* __restrict__ in, u
 }
 
 // pass D: forward DIT over the block index (rows at stride Cp), in place
-__global__ void __launch_bounds__(256) k_ntt_pass_d(u64* __restrict__ data, int K1, size_t Cp, size_t stride,
+static __global__ void __launch_bounds__(256) k_ntt_pass_d(u64* __restrict__ data, int K1, size_t Cp, size_t stride,
                                                     Tables t) {
   extern __shared__ u64 sm[];
   const int R = 1 << K1;

@@ -4,13 +4,11 @@
 // (or, test-only, g++ -x c++ -DPB254_HOSTSIM for the host-simulation library under tests/hostsim/).
 #include "../../include/pb254.h"
 #include "compat.cuh"
-#if !PB_HOSTSIM
 unsigned long long g_pb_launches = 0;
-#else
-static unsigned long long g_pb_launches = 0;
-#endif
 #include "context.cuh"
+#include "ntt.cuh"
 #include "merkle.cuh"
+#include "tracegen.h"
 
 namespace {
 thread_local std::string g_last_error;
@@ -46,6 +44,13 @@ Shape shape_for(int kind) {
     case PB254_KIND_FQ: return {16, 427, 80, 8};
   }
   throw Pb254Error(PB254_E_BAD_ARG, "unknown STARK kind");
+}
+
+void throw_trace_error(int herr) {
+  if (herr == tg::ERR_NOT_CANONICAL) throw Pb254Error(PB254_E_NOT_CANONICAL, "input coordinate >= p");
+  if (herr == tg::ERR_INFINITY)
+    throw Pb254Error(PB254_E_INFINITY, "an intermediate sum is the point at infinity (a = -b), unsupported by design");
+  if (herr) throw Pb254Error(PB254_E_BAD_ARG, "trace generation: witness consistency check failed");
 }
 
 struct PermuteK {
@@ -187,6 +192,36 @@ int pb254_commit(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n, ui
     if (digests_out) pb_d2h(digests_out, dig, nd * 32, c->stream);
     pb_sync(c->stream);
     c->times.resolve();
+  });
+}
+
+int pb254_generate_trace(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
+                         size_t min_rows, uint64_t* cols_out) {
+  return guarded([&] {
+    pb_set_device(c->device);
+    tg::Layout l = tg::layout_for(shape_for(kind).width == 0 ? 0 : kind);
+    size_t n_rows = pb254_trace_rows(n_inputs, min_rows);
+    if (n_rows < 65536) throw Pb254Error(PB254_E_BAD_ARG, "trace must have at least 2^16 rows (range-check table)");
+    size_t tbytes = (size_t)l.width * n_rows * 8;
+    c->arena.reserve(tbytes + tg::scratch_bytes(kind, n_inputs) + n_inputs * (l.in_words + 1) * 8 + 65536);
+    c->arena.reset();
+    u64* d_trace = c->arena.alloc_n<u64>((size_t)l.width * n_rows);
+    u64* d_in = c->arena.alloc_n<u64>(n_inputs * l.in_words + 1);
+    u64* d_ts = c->arena.alloc_n<u64>(n_inputs + 1);
+    int* d_err = c->arena.alloc_n<int>(1);
+    pb_h2d(d_in, inputs, n_inputs * l.in_words * 8, c->stream);
+    pb_h2d(d_ts, timestamps, n_inputs * 8, c->stream);
+    pb_memset(d_err, 0, sizeof(int), c->stream);
+    c->times.clear();
+    int t0 = c->times.begin("tracegen", c->stream);
+    tg::generate(c->arena, kind, d_in, d_ts, n_inputs, n_rows, d_trace, d_err, c->stream);
+    c->times.end(t0, c->stream);
+    int herr = 0;
+    pb_d2h(&herr, d_err, sizeof(int), c->stream);
+    pb_d2h(cols_out, d_trace, tbytes, c->stream);
+    pb_sync(c->stream);
+    c->times.resolve();
+    throw_trace_error(herr);
   });
 }
 

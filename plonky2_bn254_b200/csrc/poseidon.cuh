@@ -24,7 +24,7 @@ static const u64 RC[N_ROUNDS * WIDTH] = {
 static const u64 RC_HOST[N_ROUNDS * WIDTH] = {
 #include "poseidon_constants.inc"
 };
-__constant__ u64 RC_DEV[N_ROUNDS * WIDTH] = {
+static __constant__ u64 RC_DEV[N_ROUNDS * WIDTH] = {
 #include "poseidon_constants.inc"
 };
 #ifdef __CUDA_ARCH__

@@ -163,3 +163,15 @@ class Context:
         self.L.check(self.L.lib.pb254_commit(self._h, _p(v), C.c_size_t(cols), C.c_size_t(n), C.c_uint32(rate_bits),
                                              C.c_uint32(cap_height), C.c_int(int(from_coeffs)), _p(cap), _p(dig)))
         return (cap, dig) if want_digests else cap
+
+    # ---- trace generation -----------------------------------------------------------------
+    def generate_trace(self, kind, inputs, timestamps, min_rows=1 << 16):
+        inputs = _u64(inputs)
+        timestamps = _u64(timestamps)
+        k = inputs.shape[0]
+        assert inputs.shape[1] == self.L.input_words(kind)
+        n = self.L.trace_rows(k, min_rows)
+        cols = np.empty((self.L.trace_width(kind), n), dtype=np.uint64)
+        self.L.check(self.L.lib.pb254_generate_trace(self._h, C.c_int(kind), _p(inputs), _p(timestamps), C.c_size_t(k),
+                                                     C.c_size_t(min_rows), _p(cols)))
+        return cols
