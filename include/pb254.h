@@ -95,6 +95,27 @@ int pb254_commit(pb254_ctx* ctx, const uint64_t* values, size_t cols, size_t n, 
 int pb254_generate_trace(pb254_ctx* ctx, int kind, const uint64_t* inputs, const uint64_t* timestamps,
                          size_t n_inputs, size_t min_rows, uint64_t* cols_out);
 
+/* ---- proving ------------------------------------------------------------------------------- */
+/* generate_trace + prove in one call, the body of run_once between
+ * src/generators/g1/stark_proof.rs:154 and :163; the trace stays on the device.
+ * cfg == NULL selects StarkConfig::standard_fast_config(). The proof-of-work witness is the MINIMAL
+ * one (the reference's rayon find_any returns an arbitrary valid witness). */
+int pb254_prove(pb254_ctx* ctx, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
+                size_t min_rows, const pb254_config* cfg, int keep_debug, pb254_proof** out);
+/* prove(stark, config, trace, ctls, public_inputs = []) on a host trace, column-major
+ * pb254_trace_width(kind) x n_rows (src/starks/common/prover.rs:18-30). */
+int pb254_prove_trace(pb254_ctx* ctx, int kind, const uint64_t* trace_cols, size_t n_rows, const pb254_config* cfg,
+                      int keep_debug, pb254_proof** out);
+void pb254_proof_free(pb254_proof* proof);
+/* Serialized StarkProofWithMetadata: little-endian u64 words, field order of SURVEY.md C.7 behind a
+ * 10-word header {magic, kind, degree_bits, config[7]} (layout in DESIGN.md). */
+size_t pb254_proof_words(const pb254_proof* proof);
+const uint64_t* pb254_proof_data(const pb254_proof* proof);
+/* intermediate artefacts for parity tests (only when keep_debug != 0): which = 0 auxiliary values
+ * (A x n), 1 quotient chunk coefficients (2*num_challenges x n), 2 challenges, 3 query indices */
+size_t pb254_proof_debug_words(const pb254_proof* proof, int which);
+const uint64_t* pb254_proof_debug_data(const pb254_proof* proof, int which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,11 @@ unsigned long long g_pb_launches = 0;
 #include "ntt.cuh"
 #include "merkle.cuh"
 #include "tracegen.h"
+#include "prover.cuh"
+
+struct pb254_proof {
+  prover::ProofData data;
+};
 
 namespace {
 thread_local std::string g_last_error;
@@ -223,6 +228,107 @@ int pb254_generate_trace(pb254_ctx* c, int kind, const uint64_t* inputs, const u
     c->times.resolve();
     throw_trace_error(herr);
   });
+}
+
+// generate_trace + prove in one call: what run_once does between
+// src/generators/g1/stark_proof.rs:154 and :163. The trace never leaves the device.
+int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
+                size_t min_rows, const pb254_config* cfg_in, int keep_debug, pb254_proof** out) {
+  return guarded([&] {
+    if (!out) throw Pb254Error(PB254_E_BAD_ARG, "null out pointer");
+    pb_set_device(c->device);
+    pb254_config cfg;
+    if (cfg_in)
+      cfg = *cfg_in;
+    else
+      pb254_config_standard_fast(&cfg);
+    prover::validate_config(cfg);
+    tg::Layout l = tg::layout_for(shape_for(kind).width ? kind : 0);
+    size_t n_rows = pb254_trace_rows(n_inputs, min_rows);
+    if (n_rows < 65536) throw Pb254Error(PB254_E_BAD_ARG, "trace must have at least 2^16 rows (range-check table)");
+    size_t twords = (size_t)l.width * n_rows;
+    size_t tg_bytes = tg::scratch_bytes(kind, n_inputs) + n_inputs * (l.in_words + 1) * 8 + 65536;
+    size_t pv_bytes = prover::workspace_bytes(kind, n_rows, cfg);
+    c->arena.reserve(twords * 8 + (tg_bytes > pv_bytes ? tg_bytes : pv_bytes) + 65536);
+    c->arena.reset();
+    c->times.clear();
+    u64* d_trace = c->arena.alloc_n<u64>(twords);
+    size_t mark = c->arena.off;
+    {
+      prover::Stage st(c, "tracegen");
+      u64* d_in = c->arena.alloc_n<u64>(n_inputs * l.in_words + 1);
+      u64* d_ts = c->arena.alloc_n<u64>(n_inputs + 1);
+      int* d_err = c->arena.alloc_n<int>(1);
+      pb_h2d(d_in, inputs, n_inputs * l.in_words * 8, c->stream);
+      pb_h2d(d_ts, timestamps, n_inputs * 8, c->stream);
+      pb_memset(d_err, 0, sizeof(int), c->stream);
+      tg::generate(c->arena, kind, d_in, d_ts, n_inputs, n_rows, d_trace, d_err, c->stream);
+      int herr = 0;
+      pb_d2h(&herr, d_err, sizeof(int), c->stream);
+      pb_sync(c->stream);
+      throw_trace_error(herr);
+    }
+    c->arena.off = mark;
+    pb254_proof* pf = new pb254_proof();
+    try {
+      prover::prove_device(c, kind, d_trace, n_rows, cfg, pf->data, keep_debug != 0);
+    } catch (...) {
+      delete pf;
+      throw;
+    }
+    pb_sync(c->stream);
+    c->times.resolve();
+    *out = pf;
+  });
+}
+
+// prove(stark, config, trace, ...) on a host trace (column-major width x n_rows), the literal
+// signature of src/starks/common/prover.rs:18-30.
+int pb254_prove_trace(pb254_ctx* c, int kind, const uint64_t* trace_cols, size_t n_rows, const pb254_config* cfg_in,
+                      int keep_debug, pb254_proof** out) {
+  return guarded([&] {
+    if (!out) throw Pb254Error(PB254_E_BAD_ARG, "null out pointer");
+    pb_set_device(c->device);
+    pb254_config cfg;
+    if (cfg_in)
+      cfg = *cfg_in;
+    else
+      pb254_config_standard_fast(&cfg);
+    prover::validate_config(cfg);
+    tg::Layout l = tg::layout_for(shape_for(kind).width ? kind : 0);
+    size_t twords = (size_t)l.width * n_rows;
+    c->arena.reserve(twords * 8 + prover::workspace_bytes(kind, n_rows, cfg) + 65536);
+    c->arena.reset();
+    c->times.clear();
+    u64* d_trace = c->arena.alloc_n<u64>(twords);
+    pb_h2d(d_trace, trace_cols, twords * 8, c->stream);
+    pb254_proof* pf = new pb254_proof();
+    try {
+      prover::prove_device(c, kind, d_trace, n_rows, cfg, pf->data, keep_debug != 0);
+    } catch (...) {
+      delete pf;
+      throw;
+    }
+    pb_sync(c->stream);
+    c->times.resolve();
+    *out = pf;
+  });
+}
+
+void pb254_proof_free(pb254_proof* p) { delete p; }
+size_t pb254_proof_words(const pb254_proof* p) { return p->data.blob.size(); }
+const uint64_t* pb254_proof_data(const pb254_proof* p) { return p->data.blob.data(); }
+// debug artefacts kept when keep_debug != 0: 0 auxiliary values (A x n), 1 quotient chunk coefficients
+// (2*num_challenges x n), 2 challenges [betas, gammas, alphas, zeta, fri_alpha, fri_betas], 3 query indices
+size_t pb254_proof_debug_words(const pb254_proof* p, int which) {
+  const std::vector<u64>* v = which == 0 ? &p->data.dbg_aux : which == 1 ? &p->data.dbg_chunks
+                            : which == 2 ? &p->data.dbg_challenges : which == 3 ? &p->data.dbg_indices : nullptr;
+  return v ? v->size() : 0;
+}
+const uint64_t* pb254_proof_debug_data(const pb254_proof* p, int which) {
+  const std::vector<u64>* v = which == 0 ? &p->data.dbg_aux : which == 1 ? &p->data.dbg_chunks
+                            : which == 2 ? &p->data.dbg_challenges : which == 3 ? &p->data.dbg_indices : nullptr;
+  return v ? v->data() : nullptr;
 }
 
 }  // extern "C"

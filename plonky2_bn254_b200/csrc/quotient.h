@@ -1,0 +1,35 @@
+// K8 `quotient_eval_{g1,g2,fq}` interface. See quotient_impl.cuh.
+#pragma once
+#include "context.cuh"
+#include "aux.cuh"
+
+namespace quot {
+
+struct Params {
+  const u64* tr;      // trace LDE, column-major, stride tr_stride
+  size_t tr_stride;
+  const u64* ax;      // auxiliary LDE, column-major
+  size_t ax_stride;
+  u64* out;           // nch x size, natural order: combined constraints / Z_H at 7 * w^i
+  const u64* weights; // [K][nch]: alpha_j^(K-1-k)
+  size_t size;        // quotient domain size = 2 n
+  int log_size;
+  size_t step;        // LDE index of quotient point i is i * step  (2^(rate_bits - 1))
+  ntt::Tables t;
+  u64 g;              // root of unity of order n
+  u64 g_inv;          // "last" = g^-1
+  u64 n_field;        // n as a field element
+  u64 zh[2];          // Z_H at even / odd points: 7^n * (+-1) - 1
+  u64 zh_inv[2];
+  aux::Challenges ch;
+  int* err;           // set to 1 if the emitted constraint count disagrees with the weight table
+};
+
+// constraints per (local, next) row pair incl. lookups and CTLs for `nch` challenges
+int num_constraints(int kind, int nch);
+
+void run_g1(const Params& p, pbStream s);
+void run_g2(const Params& p, pbStream s);
+void run_fq(const Params& p, pbStream s);
+
+}  // namespace quot

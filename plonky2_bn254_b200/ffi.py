@@ -68,9 +68,15 @@ class Library:
         L.pb254_timing_name.restype = C.c_char_p
         L.pb254_timing_ms.argtypes = [C.c_void_p, C.c_int]
         L.pb254_timing_ms.restype = C.c_double
-        for name in ("pb254_proof_words",):
-            if hasattr(L, name):
-                getattr(L, name).restype = C.c_size_t
+        L.pb254_proof_words.restype = C.c_size_t
+        L.pb254_proof_words.argtypes = [C.c_void_p]
+        L.pb254_proof_data.restype = C.POINTER(C.c_uint64)
+        L.pb254_proof_data.argtypes = [C.c_void_p]
+        L.pb254_proof_debug_words.restype = C.c_size_t
+        L.pb254_proof_debug_words.argtypes = [C.c_void_p, C.c_int]
+        L.pb254_proof_debug_data.restype = C.POINTER(C.c_uint64)
+        L.pb254_proof_debug_data.argtypes = [C.c_void_p, C.c_int]
+        L.pb254_proof_free.argtypes = [C.c_void_p]
 
     def check(self, rc):
         if rc != 0:
@@ -175,3 +181,59 @@ class Context:
         self.L.check(self.L.lib.pb254_generate_trace(self._h, C.c_int(kind), _p(inputs), _p(timestamps), C.c_size_t(k),
                                                      C.c_size_t(min_rows), _p(cols)))
         return cols
+
+    # ---- proving --------------------------------------------------------------------------
+    def prove(self, kind, inputs, timestamps, min_rows=1 << 16, config: Config | None = None, keep_debug=False):
+        """generate_trace + prove on the device; returns a :class:`Proof`."""
+        inputs = _u64(inputs)
+        timestamps = _u64(timestamps)
+        assert inputs.ndim == 2 and inputs.shape[1] == self.L.input_words(kind)
+        h = C.c_void_p()
+        self.L.check(self.L.lib.pb254_prove(self._h, C.c_int(kind), _p(inputs), _p(timestamps),
+                                            C.c_size_t(inputs.shape[0]), C.c_size_t(min_rows),
+                                            C.byref(config) if config is not None else None, C.c_int(int(keep_debug)),
+                                            C.byref(h)))
+        return Proof(self.L, h)
+
+    def prove_trace(self, kind, trace_cols, config: Config | None = None, keep_debug=False):
+        t = _u64(trace_cols)
+        assert t.shape[0] == self.L.trace_width(kind)
+        h = C.c_void_p()
+        self.L.check(self.L.lib.pb254_prove_trace(self._h, C.c_int(kind), _p(t), C.c_size_t(t.shape[1]),
+                                                  C.byref(config) if config is not None else None,
+                                                  C.c_int(int(keep_debug)), C.byref(h)))
+        return Proof(self.L, h)
+
+
+class Proof:
+    """Owned pb254_proof handle."""
+
+    def __init__(self, library: Library, handle):
+        self.L = library
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.lib.pb254_proof_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def words(self) -> np.ndarray:
+        n = self.L.lib.pb254_proof_words(self._h)
+        p = self.L.lib.pb254_proof_data(self._h)
+        return np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+    def bytes(self) -> bytes:
+        return self.words().tobytes()
+
+    def debug(self, which: int) -> np.ndarray:
+        n = self.L.lib.pb254_proof_debug_words(self._h, which)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint64)
+        p = self.L.lib.pb254_proof_debug_data(self._h, which)
+        return np.ctypeslib.as_array(p, shape=(n,)).copy()
