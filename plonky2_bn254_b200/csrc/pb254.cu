@@ -322,12 +322,12 @@ const uint64_t* pb254_proof_data(const pb254_proof* p) { return p->data.blob.dat
 // (2*num_challenges x n), 2 challenges [betas, gammas, alphas, zeta, fri_alpha, fri_betas], 3 query indices
 size_t pb254_proof_debug_words(const pb254_proof* p, int which) {
   const std::vector<u64>* v = which == 0 ? &p->data.dbg_aux : which == 1 ? &p->data.dbg_chunks
-                            : which == 2 ? &p->data.dbg_challenges : which == 3 ? &p->data.dbg_indices : nullptr;
+                            : which == 2 ? &p->data.dbg_challenges : which == 3 ? &p->data.dbg_indices : which == 4 ? &p->data.dbg_qvals : which == 5 ? &p->data.dbg_groups : nullptr;
   return v ? v->size() : 0;
 }
 const uint64_t* pb254_proof_debug_data(const pb254_proof* p, int which) {
   const std::vector<u64>* v = which == 0 ? &p->data.dbg_aux : which == 1 ? &p->data.dbg_chunks
-                            : which == 2 ? &p->data.dbg_challenges : which == 3 ? &p->data.dbg_indices : nullptr;
+                            : which == 2 ? &p->data.dbg_challenges : which == 3 ? &p->data.dbg_indices : which == 4 ? &p->data.dbg_qvals : which == 5 ? &p->data.dbg_groups : nullptr;
   return v ? v->data() : nullptr;
 }
 

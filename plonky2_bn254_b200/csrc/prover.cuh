@@ -72,7 +72,7 @@ static const u64 PROOF_MAGIC = 0x31465250343532ULL | ((u64)'B' << 56);
 
 struct ProofData {
   std::vector<u64> blob;
-  std::vector<u64> dbg_aux, dbg_chunks, dbg_challenges, dbg_indices;
+  std::vector<u64> dbg_aux, dbg_chunks, dbg_challenges, dbg_indices, dbg_qvals, dbg_groups;
 };
 
 static inline void validate_config(const pb254_config& c) {
@@ -214,6 +214,7 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   u64* qcoef = ar.alloc_n<u64>((size_t)nch * qsize);
   int* d_err = ar.alloc_n<int>(1);
   pb_memset(d_err, 0, sizeof(int), s);
+  u64* d_dbg_groups = nullptr;
   {
     Stage st(c, "quotient eval");
     quot::Params qp;
@@ -238,6 +239,13 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     qp.zh_inv[1] = gl::inv(qp.zh[1]);
     qp.ch = chal;
     qp.err = d_err;
+    qp.dbg = nullptr;
+    qp.dbg_point = 5;
+    if (keep_debug) {
+      qp.dbg = ar.alloc_n<u64>(4096);
+      pb_memset(qp.dbg, 0, 4096 * 8, s);
+    }
+    d_dbg_groups = qp.dbg;
     if (kind == 0)
       quot::run_g1(qp, s);
     else if (kind == 1)
@@ -511,6 +519,10 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     pb_d2h(out.dbg_aux.data(), aux_vals, (size_t)A * n * 8, s);
     out.dbg_chunks.resize((size_t)Q * n);
     pb_d2h(out.dbg_chunks.data(), qcoef, (size_t)Q * n * 8, s);
+    out.dbg_qvals.resize((size_t)nch * qsize);
+    pb_d2h(out.dbg_qvals.data(), qvals, (size_t)nch * qsize * 8, s);
+    out.dbg_groups.resize(4096);
+    pb_d2h(out.dbg_groups.data(), d_dbg_groups, 4096 * 8, s);
     pb_sync(s);
     auto& d = out.dbg_challenges;
     d.clear();

@@ -23,6 +23,8 @@ struct Params {
   u64 zh_inv[2];
   aux::Challenges ch;
   int* err;           // set to 1 if the emitted constraint count disagrees with the weight table
+  u64* dbg;           // keep_debug only: running total[0] after every constraint group of point dbg_point
+  size_t dbg_point;
 };
 
 // constraints per (local, next) row pair incl. lookups and CTLs for `nch` challenges

@@ -41,6 +41,8 @@ struct Emit {
   int nch, k;
   gl::Acc acc[aux::MAXCH];
   u64 total[aux::MAXCH];
+  u64* dbg = nullptr;
+  int ng = 0;
   PB_HD Emit(const u64* w_, int nch_) : w(w_), nch(nch_), k(0) {
 #pragma unroll
     for (int j = 0; j < aux::MAXCH; j++) total[j] = 0;
@@ -59,13 +61,14 @@ struct Emit {
         total[j] = gl::add(total[j], gl::mul(f, acc[j].reduce()));
         acc[j] = gl::Acc();
       }
+    if (dbg) dbg[ng++] = total[0];
   }
 };
 
 #if PB_HOSTSIM
 #define Q_NOINLINE static inline
 #else
-#define Q_NOINLINE static __device__ __noinline__
+#define Q_NOINLINE static __host__ __device__ __noinline__
 #endif
 
 // The limb-polynomial helpers below are deliberately NOT inlined and keep real loops: a STARK has
@@ -114,6 +117,15 @@ Q_NOINLINE void mz_values(const u64* tr, size_t stride, size_t i0, const u64* in
   }
 }
 
+// All per-thread scratch arrays live in ONE function-scope object. They used to be block-scope locals
+// of the (force-inlined) helpers; nvcc 12.9's stack colouring then overlapped two arrays that are live
+// at the same time (a block-scope d0[31] and ext_conv's t[31] shared one slot in the G2 kernel), which
+// made the G2 quotient wrong on the device only. One object has one lifetime, so nothing can overlap.
+struct Scratch {
+  u64 l0[16], l1[16], u0[16], u1[16];
+  u64 c0[31], c1[31], d0[31], d1[31], t[31], v[33];
+};
+
 template <int KIND>
 struct QuotientK {
   Params p;
@@ -122,16 +134,15 @@ struct QuotientK {
   PB_HD u64 TL(size_t i0, int c) const { return p.tr[(size_t)c * p.tr_stride + i0]; }
 
   // eval_modulus_zero: 33 terms (the caller closes the group with the filter)
-  PB_HD void mz(Emit& E, size_t i0, const u64* in, int auxcol) const {
-    u64 v[33];
-    mz_values(p.tr, p.tr_stride, i0, in, auxcol, v);
+  PB_HD void mz(Emit& E, Scratch& S, size_t i0, const u64* in, int auxcol) const {
+    mz_values(p.tr, p.tr_stride, i0, in, auxcol, S.v);
 #pragma unroll 1
-    for (int k = 0; k < 33; k++) E.term(v[k]);
+    for (int k = 0; k < 33; k++) E.term(S.v[k]);
   }
 
   // eval_is_modulus_zero: 49 terms under one filter. input columns: in_b - in_a (16 limbs)
-  PB_HD void imz(Emit& E, size_t i0, int col_b, int col_a, int is_zero_col, int auxcol) const {
-    u64 dx[16], iv[16], in[31];
+  PB_HD void imz(Emit& E, Scratch& S, size_t i0, int col_b, int col_a, int is_zero_col, int auxcol) const {
+    u64 *dx = S.u0, *iv = S.u1, *in = S.c0;
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       dx[i] = gl::sub(TL(i0, col_b + i), TL(i0, col_a + i));
@@ -140,7 +151,7 @@ struct QuotientK {
     conv31(dx, iv, in);
     u64 is_zero = TL(i0, is_zero_col);
     in[0] = gl::add(in[0], gl::sub(is_zero, 1));
-    mz(E, i0, in, auxcol + 16);
+    mz(E, S, i0, in, auxcol + 16);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) E.term(gl::mul(dx[i], is_zero));
   }
@@ -150,14 +161,14 @@ struct QuotientK {
     for (int i = 0; i < 16; i++) out[i] = TL(i0, col + i);
   }
 
-  PB_HD void add_g1(Emit& E, size_t i0, u64 filter) const {
+  PB_HD void add_g1(Emit& E, Scratch& S, size_t i0, u64 filter) const {
     const int A = Y::aux, a = Y::a, b = Y::b, c = Y::c;
-    imz(E, i0, b, a, A, A + 1);
+    imz(E, S, i0, b, a, A, A + 1);
     E.end_group(filter);
     u64 is_x_eq = TL(i0, A), is_x_eq_filter = TL(i0, A + 97);
     E.term(gl::sub(gl::mul(filter, is_x_eq), is_x_eq_filter));
     E.end_group(1);
-    u64 lam[16], t0[16], in[31], in2[31];
+    u64 *lam = S.l0, *t0 = S.u0, *in = S.c0, *in2 = S.d0;
     ld16(i0, A + 98, lam);
     // a.x != b.x : lambda * dx - (b.y - a.y)
 #pragma unroll 1
@@ -165,7 +176,7 @@ struct QuotientK {
     conv31(lam, t0, in);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) in[i] = gl::sub(in[i], gl::sub(TL(i0, b + 16 + i), TL(i0, a + 16 + i)));
-    mz(E, i0, in, A + 114);
+    mz(E, S, i0, in, A + 114);
     E.end_group(gl::sub(filter, is_x_eq_filter));
     // a.x == b.x : 2 lambda a.y - 3 a.x^2
     ld16(i0, a, t0);
@@ -174,7 +185,7 @@ struct QuotientK {
     conv31(lam, t0, in);
 #pragma unroll 1
     for (int i = 0; i < 31; i++) in[i] = gl::sub(gl::dbl(in[i]), gl::add(gl::dbl(in2[i]), in2[i]));
-    mz(E, i0, in, A + 114);
+    mz(E, S, i0, in, A + 114);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) E.term(gl::sub(TL(i0, a + 16 + i), TL(i0, b + 16 + i)));
     E.end_group(is_x_eq_filter);
@@ -183,21 +194,21 @@ struct QuotientK {
 #pragma unroll 1
     for (int i = 0; i < 16; i++)
       in[i] = gl::sub(in[i], gl::add(gl::add(TL(i0, a + i), TL(i0, b + i)), TL(i0, c + i)));
-    mz(E, i0, in, A + 194);
+    mz(E, S, i0, in, A + 194);
     // y : lambda (c.x - a.x) + c.y + a.y
 #pragma unroll 1
     for (int i = 0; i < 16; i++) t0[i] = gl::sub(TL(i0, c + i), TL(i0, a + i));
     conv31(lam, t0, in);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) in[i] = gl::add(in[i], gl::add(TL(i0, c + 16 + i), TL(i0, a + 16 + i)));
-    mz(E, i0, in, A + 274);
+    mz(E, S, i0, in, A + 274);
     E.end_group(filter);
   }
 
   // (x * y) over Fq2 on limb polynomials: c0 = x0 y0 - x1 y1, c1 = x0 y1 + x1 y0
-  PB_HD void ext_conv(const u64 x0[16], const u64 x1[16], const u64 y0[16], const u64 y1[16], u64 c0[31],
+  PB_HD void ext_conv(Scratch& S, const u64 x0[16], const u64 x1[16], const u64 y0[16], const u64 y1[16], u64 c0[31],
                       u64 c1[31]) const {
-    u64 t[31];
+    u64* t = S.t;
     conv31(x0, y0, c0);
     conv31(x1, y1, t);
 #pragma unroll 1
@@ -208,17 +219,17 @@ struct QuotientK {
     for (int i = 0; i < 31; i++) c1[i] = gl::add(c1[i], t[i]);
   }
 
-  PB_HD void add_g2(Emit& E, size_t i0, u64 filter) const {
+  PB_HD void add_g2(Emit& E, Scratch& S, size_t i0, u64 filter) const {
     const int A = Y::aux, a = Y::a, b = Y::b, c = Y::c;  // points: x.c0 | x.c1 | y.c0 | y.c1
     u64 is_x_eq = TL(i0, A), z0 = TL(i0, A + 1), z1 = TL(i0, A + 2);
     E.term(gl::sub(gl::mul(z0, z1), is_x_eq));
-    imz(E, i0, b, a, A + 1, A + 3);
-    imz(E, i0, b + 16, a + 16, A + 2, A + 99);
+    imz(E, S, i0, b, a, A + 1, A + 3);
+    imz(E, S, i0, b + 16, a + 16, A + 2, A + 99);
     E.end_group(filter);
     u64 is_x_eq_filter = TL(i0, A + 195);
     E.term(gl::sub(gl::mul(filter, is_x_eq), is_x_eq_filter));
     E.end_group(1);
-    u64 l0[16], l1[16], u0[16], u1[16], c0[31], c1[31];
+    u64 *l0 = S.l0, *l1 = S.l1, *u0 = S.u0, *u1 = S.u1, *c0 = S.c0, *c1 = S.c1, *d0 = S.d0, *d1 = S.d1;
     ld16(i0, A + 196, l0);
     ld16(i0, A + 212, l1);
     // lambda * dx - dy
@@ -227,69 +238,68 @@ struct QuotientK {
       u0[i] = gl::sub(TL(i0, b + i), TL(i0, a + i));
       u1[i] = gl::sub(TL(i0, b + 16 + i), TL(i0, a + 16 + i));
     }
-    ext_conv(l0, l1, u0, u1, c0, c1);
+    ext_conv(S, l0, l1, u0, u1, c0, c1);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       c0[i] = gl::sub(c0[i], gl::sub(TL(i0, b + 32 + i), TL(i0, a + 32 + i)));
       c1[i] = gl::sub(c1[i], gl::sub(TL(i0, b + 48 + i), TL(i0, a + 48 + i)));
     }
-    mz(E, i0, c0, A + 228);
-    mz(E, i0, c1, A + 308);
+    mz(E, S, i0, c0, A + 228);
+    mz(E, S, i0, c1, A + 308);
     E.end_group(gl::sub(filter, is_x_eq_filter));
     // 2 lambda a.y - 3 a.x^2
     {
-      u64 d0[31], d1[31];
       ld16(i0, a, u0);
       ld16(i0, a + 16, u1);
-      ext_conv(u0, u1, u0, u1, d0, d1);
+      ext_conv(S, u0, u1, u0, u1, d0, d1);
       ld16(i0, a + 32, u0);
       ld16(i0, a + 48, u1);
-      ext_conv(l0, l1, u0, u1, c0, c1);
+      ext_conv(S, l0, l1, u0, u1, c0, c1);
 #pragma unroll 1
       for (int i = 0; i < 31; i++) {
         c0[i] = gl::sub(gl::dbl(c0[i]), gl::add(gl::dbl(d0[i]), d0[i]));
         c1[i] = gl::sub(gl::dbl(c1[i]), gl::add(gl::dbl(d1[i]), d1[i]));
       }
     }
-    mz(E, i0, c0, A + 228);
-    mz(E, i0, c1, A + 308);
+    mz(E, S, i0, c0, A + 228);
+    mz(E, S, i0, c1, A + 308);
 #pragma unroll 2
     for (int i = 0; i < 32; i++) E.term(gl::sub(TL(i0, a + 32 + i), TL(i0, b + 32 + i)));
     E.end_group(is_x_eq_filter);
     // x
-    ext_conv(l0, l1, l0, l1, c0, c1);
+    ext_conv(S, l0, l1, l0, l1, c0, c1);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       c0[i] = gl::sub(c0[i], gl::add(gl::add(TL(i0, a + i), TL(i0, b + i)), TL(i0, c + i)));
       c1[i] = gl::sub(c1[i], gl::add(gl::add(TL(i0, a + 16 + i), TL(i0, b + 16 + i)), TL(i0, c + 16 + i)));
     }
-    mz(E, i0, c0, A + 388);
-    mz(E, i0, c1, A + 468);
+    mz(E, S, i0, c0, A + 388);
+    mz(E, S, i0, c1, A + 468);
     // y
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       u0[i] = gl::sub(TL(i0, c + i), TL(i0, a + i));
       u1[i] = gl::sub(TL(i0, c + 16 + i), TL(i0, a + 16 + i));
     }
-    ext_conv(l0, l1, u0, u1, c0, c1);
+    ext_conv(S, l0, l1, u0, u1, c0, c1);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       c0[i] = gl::add(c0[i], gl::add(TL(i0, c + 32 + i), TL(i0, a + 32 + i)));
       c1[i] = gl::add(c1[i], gl::add(TL(i0, c + 48 + i), TL(i0, a + 48 + i)));
     }
-    mz(E, i0, c0, A + 548);
-    mz(E, i0, c1, A + 628);
+    mz(E, S, i0, c0, A + 548);
+    mz(E, S, i0, c1, A + 628);
     E.end_group(filter);
   }
 
-  PB_HD void mul_fq(Emit& E, size_t i0, u64 filter) const {
-    u64 x[16], y[16], in[31];
+  PB_HD void mul_fq(Emit& E, Scratch& S, size_t i0, u64 filter) const {
+    u64 *x = S.u0, *y = S.u1, *in = S.c0;
     ld16(i0, Y::a, x);
     ld16(i0, Y::b, y);
     conv31(x, y, in);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) in[i] = gl::sub(in[i], TL(i0, Y::c + i));
-    mz(E, i0, in, Y::aux);
+    mz(E, S, i0, in, Y::aux);
     E.end_group(filter);
   }
 
@@ -311,14 +321,16 @@ struct QuotientK {
     const u64 l_last = gl::mul(z_h, gl::inv(gl::mul(p.n_field, gl::sub(gl::mul(p.g, x), 1))));
 
     Emit E(p.weights, nch);
+    if (p.dbg && i == p.dbg_point) E.dbg = p.dbg;
     const u64 filter = TL(i0, Y::filter);
     const u64 is_first = TL(i0, Y::rf), is_last = TL(i0, Y::rf + 1);
+    Scratch S;
     if (KIND == 0)
-      add_g1(E, i0, filter);
+      add_g1(E, S, i0, filter);
     else if (KIND == 1)
-      add_g2(E, i0, filter);
+      add_g2(E, S, i0, filter);
     else
-      mul_fq(E, i0, filter);
+      mul_fq(E, S, i0, filter);
     // first round
     E.term(gl::sub(TL(i0, Y::flag_op), 1));
     eq_terms(E, i0, Y::reg0, i0, Y::b, L);
