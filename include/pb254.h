@@ -102,6 +102,10 @@ int pb254_generate_trace(pb254_ctx* ctx, int kind, const uint64_t* inputs, const
  * one (the reference's rayon find_any returns an arbitrary valid witness). */
 int pb254_prove(pb254_ctx* ctx, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
                 size_t min_rows, const pb254_config* cfg, int keep_debug, pb254_proof** out);
+/* pb254_prove with `d_inputs` / `d_timestamps` already resident in the memory of the context's GPU
+ * (same wire format); the batched-pipeline form, where a producer kernel wrote the work items. */
+int pb254_prove_dev(pb254_ctx* ctx, int kind, const uint64_t* d_inputs, const uint64_t* d_timestamps,
+                    size_t n_inputs, size_t min_rows, const pb254_config* cfg, int keep_debug, pb254_proof** out);
 /* prove(stark, config, trace, ctls, public_inputs = []) on a host trace, column-major
  * pb254_trace_width(kind) x n_rows (src/starks/common/prover.rs:18-30). */
 int pb254_prove_trace(pb254_ctx* ctx, int kind, const uint64_t* trace_cols, size_t n_rows, const pb254_config* cfg,

@@ -232,10 +232,12 @@ int pb254_generate_trace(pb254_ctx* c, int kind, const uint64_t* inputs, const u
 
 // generate_trace + prove in one call: what run_once does between
 // src/generators/g1/stark_proof.rs:154 and :163. The trace never leaves the device.
-int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
-                size_t min_rows, const pb254_config* cfg_in, int keep_debug, pb254_proof** out) {
+static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
+                             size_t min_rows, const pb254_config* cfg_in, int keep_debug, pb254_proof** out,
+                             bool inputs_on_device) {
   return guarded([&] {
     if (!out) throw Pb254Error(PB254_E_BAD_ARG, "null out pointer");
+    if (!c || !inputs || !timestamps || n_inputs == 0) throw Pb254Error(PB254_E_BAD_ARG, "null or empty input");
     pb_set_device(c->device);
     pb254_config cfg;
     if (cfg_in)
@@ -256,11 +258,16 @@ int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* 
     size_t mark = c->arena.off;
     {
       prover::Stage st(c, "tracegen");
-      u64* d_in = c->arena.alloc_n<u64>(n_inputs * l.in_words + 1);
-      u64* d_ts = c->arena.alloc_n<u64>(n_inputs + 1);
+      const u64 *d_in = inputs, *d_ts = timestamps;
+      if (!inputs_on_device) {
+        u64* hin = c->arena.alloc_n<u64>(n_inputs * l.in_words + 1);
+        u64* hts = c->arena.alloc_n<u64>(n_inputs + 1);
+        pb_h2d(hin, inputs, n_inputs * l.in_words * 8, c->stream);
+        pb_h2d(hts, timestamps, n_inputs * 8, c->stream);
+        d_in = hin;
+        d_ts = hts;
+      }
       int* d_err = c->arena.alloc_n<int>(1);
-      pb_h2d(d_in, inputs, n_inputs * l.in_words * 8, c->stream);
-      pb_h2d(d_ts, timestamps, n_inputs * 8, c->stream);
       pb_memset(d_err, 0, sizeof(int), c->stream);
       tg::generate(c->arena, kind, d_in, d_ts, n_inputs, n_rows, d_trace, d_err, c->stream);
       int herr = 0;
@@ -280,6 +287,17 @@ int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* 
     c->times.resolve();
     *out = pf;
   });
+}
+
+int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
+                size_t min_rows, const pb254_config* cfg, int keep_debug, pb254_proof** out) {
+  return prove_inputs_impl(c, kind, inputs, timestamps, n_inputs, min_rows, cfg, keep_debug, out, false);
+}
+
+// Same with `inputs` / `timestamps` already resident in device memory of the context's GPU.
+int pb254_prove_dev(pb254_ctx* c, int kind, const uint64_t* d_inputs, const uint64_t* d_timestamps, size_t n_inputs,
+                    size_t min_rows, const pb254_config* cfg, int keep_debug, pb254_proof** out) {
+  return prove_inputs_impl(c, kind, d_inputs, d_timestamps, n_inputs, min_rows, cfg, keep_debug, out, true);
 }
 
 // prove(stark, config, trace, ...) on a host trace (column-major width x n_rows), the literal

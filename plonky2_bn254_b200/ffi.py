@@ -195,6 +195,17 @@ class Context:
                                             C.byref(h)))
         return Proof(self.L, h)
 
+    def prove_dev(self, kind, d_inputs_ptr: int, d_timestamps_ptr: int, n_inputs: int, min_rows=1 << 16,
+                  config: Config | None = None):
+        """pb254_prove_dev: inputs and timestamps are device pointers on this context's GPU."""
+        h = C.c_void_p()
+        self.L.check(self.L.lib.pb254_prove_dev(self._h, C.c_int(kind), C.c_void_p(d_inputs_ptr),
+                                                C.c_void_p(d_timestamps_ptr), C.c_size_t(n_inputs),
+                                                C.c_size_t(min_rows),
+                                                C.byref(config) if config is not None else None, C.c_int(0),
+                                                C.byref(h)))
+        return Proof(self.L, h)
+
     def prove_trace(self, kind, trace_cols, config: Config | None = None, keep_debug=False):
         t = _u64(trace_cols)
         assert t.shape[0] == self.L.trace_width(kind)

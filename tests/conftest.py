@@ -1,3 +1,4 @@
+import json
 import os
 import sys
 
@@ -20,6 +21,12 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx():
     """Product library on cuda:0. Fails loudly (no fallback) if the library or the GPU is missing."""
     from plonky2_bn254_b200 import ffi
@@ -36,3 +43,15 @@ def hostsim_ctx():
     ctx = ffi.Context(0, library=ffi.Library(path))
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="session")
+def fq_case(oracle):
+    """One fq_exp batch (3 exponentiations, 2^16 rows) proved by the oracle with debug artefacts; shared by
+    the CPU tests (an oracle proof of the smallest admissible trace takes tens of seconds on 8 cores)."""
+    from plonky2_bn254_b200 import inputs as I
+    inp, ts = I.make_inputs(I.KIND_FQ, 3, I.config_seed(42))
+    trace = oracle.generate_trace(I.KIND_FQ, inp, ts)
+    proof = oracle.prove(I.KIND_FQ, trace, keep_debug=True)
+    return {"kind": I.KIND_FQ, "inputs": inp, "timestamps": ts, "trace": trace, "proof": proof,
+            "words": proof.words()}
