@@ -77,6 +77,68 @@ struct LevelK {
   PB_HD void operator()(size_t i) const { parent[i] = poseidon::two_to_one(child[2 * i], child[2 * i + 1]); }
 };
 
+#if !PB_HOSTSIM
+// ---- hot kernels: split round-constant table in shared memory, grid sized to the machine -----------
+__device__ __forceinline__ void stage_rc2(u64* rc2) {
+  for (int i = threadIdx.x; i < poseidon::RC2_WORDS; i += blockDim.x) rc2[i] = poseidon::RC2_DEV[i];
+  __syncthreads();
+}
+
+// one thread per LDE row; the next 8 columns are loaded while the current permutation runs
+__global__ void __launch_bounds__(128, 6) k_leaf_hash(const u64* __restrict__ lde, size_t stride, int W, int log_n,
+                                                   Digest* __restrict__ out) {
+  __shared__ u64 rc2[poseidon::RC2_WORDS];
+  stage_rc2(rc2);
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ((size_t)1 << log_n)) return;
+  const u64* p = lde + j;
+  u64 s[12], nx[8];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  const int chunks = (W + 7) / 8;
+#pragma unroll
+  for (int k = 0; k < 8; k++) nx[k] = k < W ? p[(size_t)k * stride] : 0;
+#pragma unroll 1
+  for (int c = 0; c < chunks; c++) {
+    // hash_no_pad overwrites the first min(8, remaining) rate lanes with the chunk
+    const int len = W - 8 * c;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < len) s[k] = nx[k];
+    const u64* q = p + (size_t)(c + 1) * 8 * stride;
+    const int nlen = len - 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < nlen) nx[k] = q[(size_t)k * stride];
+    poseidon::lazy::permute(s, rc2);
+  }
+  Digest d;
+#pragma unroll
+  for (int i = 0; i < 4; i++) d.e[i] = s[i];
+  out[gl::brev32((u32)j, log_n)] = d;
+}
+
+__global__ void __launch_bounds__(128, 6) k_level(const Digest* __restrict__ child, Digest* __restrict__ parent, size_t n) {
+  __shared__ u64 rc2[poseidon::RC2_WORDS];
+  stage_rc2(rc2);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 s[12];
+  const Digest l = child[2 * i], r = child[2 * i + 1];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    s[k] = l.e[k];
+    s[4 + k] = r.e[k];
+    s[8 + k] = 0;
+  }
+  poseidon::lazy::permute(s, rc2);
+  Digest d;
+#pragma unroll
+  for (int k = 0; k < 4; k++) d.e[k] = s[k];
+  parent[i] = d;
+}
+#endif
+
 static inline size_t tree_digests(int log_n, int cap_height) {
   size_t total = 0;
   for (int l = log_n; l >= cap_height; l--) total += (size_t)1 << l;
@@ -94,8 +156,14 @@ static inline void build_levels(Digest* digests, int log_n, int cap_height, pbSt
   size_t off = 0;
   for (int l = 0; l < log_n - cap_height; l++) {
     size_t m = (size_t)1 << (log_n - l);
+#if PB_HOSTSIM
     LevelK k{digests + off, digests + off + m};
     pb_launch("merkle level", k, m / 2, s, 128);
+#else
+    k_level<<<(unsigned)((m / 2 + 127) / 128), 128, 0, s>>>(digests + off, digests + off + m, m / 2);
+    g_pb_launches++;
+    pb_check_last("merkle level");
+#endif
     off += m;
   }
 }
@@ -103,8 +171,20 @@ static inline void build_levels(Digest* digests, int log_n, int cap_height, pbSt
 // digests: tree_digests(log_n, cap_height) entries; the cap is the last 2^cap_height of them
 static inline void build_from_lde(const u64* lde, size_t stride, int W, int log_n, int cap_height, Digest* digests,
                                   pbStream s) {
+#if PB_HOSTSIM
   LeafHashK k{lde, stride, W, log_n, digests};
   pb_launch("leaf hash", k, (size_t)1 << log_n, s, 128);
+#else
+  if (W <= 4) {  // hash_or_noop: no permutation, the generic functor kernel is fine
+    LeafHashK k{lde, stride, W, log_n, digests};
+    pb_launch("leaf copy", k, (size_t)1 << log_n, s, 128);
+  } else {
+    const size_t n = (size_t)1 << log_n;
+    k_leaf_hash<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(lde, stride, W, log_n, digests);
+    g_pb_launches++;
+    pb_check_last("leaf hash");
+  }
+#endif
   build_levels(digests, log_n, cap_height, s);
 }
 static inline void build_from_rows(const u64* rows, int len, int log_n, int cap_height, Digest* digests, pbStream s) {

@@ -3,10 +3,23 @@
 // hash/poseidon.rs::Poseidon::poseidon, hashing.rs::{hash_n_to_m_no_pad, compress} (un-vendored
 // dependency; reached from src/starks/common/prover.rs:31-38 through PolynomialBatch::from_values).
 //
-// One permutation per thread, state in registers. The MDS layer uses the fact that the matrix
-// entries are < 2^6: lanes are split into 32-bit halves and the two half-sums (< 2^42) are
-// recombined and reduced once per lane, so a layer costs 2*12*12 32-bit multiply-adds plus 12
-// short reductions instead of 144 full field multiplications.
+// One permutation per thread, state in registers. Two forms with identical results:
+//   * permute_generic  canonical arithmetic everywhere (host transcript, hostsim build);
+//   * permute (device) "lazy" arithmetic tuned for the B200 integer pipes (see below); inputs must be
+//     canonical, outputs are canonical.
+//
+// Device form. The kernel is bound by instruction issue on the FMA (IMAD) and ALU pipes, so the design
+// minimises instructions per permutation (ncu: 47 k thread-instructions with canonical arithmetic) and
+// keeps the code small enough for the instruction cache:
+//   - lanes live as arbitrary u64 representatives of their residue (no conditional subtractions);
+//   - a field multiplication is 4 IMAD.WIDE.U32 plus a carry-chain reduction written in PTX
+//     (2^64 = 2^32 - 1, 2^96 = -1 mod p): add.cc / addc, no compare-and-select;
+//   - the MDS layer uses that all matrix entries are < 2^6: lanes are split into 32-bit halves and the
+//     two half-sums (< 2^42) are each 12 IMAD.WIDE.U32 accumulations; the next round's constants are
+//     folded into the accumulators' initial values, so "add round constants" costs nothing;
+//   - the optimised-partial-round factorisation of the reference implementation is NOT used: with
+//     6-bit matrix entries the dense layer (288 IMAD.WIDE) is as cheap on this machine as the sparse
+//     layer with 64-bit constants (22 full multiplications) - see DESIGN.md.
 #pragma once
 #include "gl.cuh"
 
@@ -76,7 +89,7 @@ PB_HD void mds(u64 s[12]) {
   }
 }
 
-PB_HD void permute(u64 s[12]) {
+PB_HD void permute_generic(u64 s[12]) {
 #pragma unroll 1
   for (int r = 0; r < HALF_FULL; r++) {
 #pragma unroll
@@ -96,6 +109,143 @@ PB_HD void permute(u64 s[12]) {
     for (int i = 0; i < 12; i++) s[i] = sbox(gl::add(s[i], PB_RC(r * 12 + i)));
     mds(s);
   }
+}
+
+#if !PB_HOSTSIM
+// ---- device form: lazy representatives, PTX carry chains, compact code -----------------------------
+// Split table: constant k of (round r, lane i) as RC2[(r*12 + i)*2 + {0,1}] = {k & (2^32-1), k >> 32};
+// block r = 30 is all zero. Kernels that hash a lot stage it into shared memory (RC2_WORDS u64s).
+static constexpr int RC2_WORDS = (N_ROUNDS + 1) * WIDTH * 2;
+static __constant__ u64 RC2_DEV[RC2_WORDS] = {
+#include "poseidon_constants_split.inc"
+};
+
+namespace lazy {
+
+// a * b mod p for arbitrary u64 representatives; result is an arbitrary u64 representative.
+// product words (x3 x2 x1 x0) by a mad.lo.cc / madc.hi.cc chain (ptxas: IMAD.WIDE.U32 with carry-out),
+// then  x0 + x1 2^32 + x2 2^64 + x3 2^96 == (x1:x0) - x3 + x2 (2^32 - 1)  (mod p).
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0, x1, x2, x3, m, l, h, c;\n\t"
+      "mul.lo.u32     x0, %2, %4;\n\t"
+      "mul.hi.u32     x1, %2, %4;\n\t"
+      "mad.lo.cc.u32  x1, %2, %5, x1;\n\t"
+      "madc.hi.u32    x2, %2, %5, 0;\n\t"
+      "mad.lo.cc.u32  x1, %3, %4, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+      "addc.u32       x3, 0, 0;\n\t"
+      "mad.lo.cc.u32  x2, %3, %5, x2;\n\t"
+      "madc.hi.u32    x3, %3, %5, x3;\n\t"
+      "sub.cc.u32   %0, x0, x3;\n\t"   // (x1:x0) - x3
+      "subc.cc.u32  %1, x1, 0;\n\t"
+      "subc.u32     m, 0, 0;\n\t"      // borrow ? 0xffffffff : 0
+      "sub.cc.u32   %0, %0, m;\n\t"    // wrapped by 2^64: subtract 2^32 - 1 (cannot borrow again)
+      "subc.u32     %1, %1, 0;\n\t"
+      "sub.cc.u32   l, 0, x2;\n\t"     // x2 (2^32 - 1) = (x2 << 32) - x2
+      "subc.u32     h, x2, 0;\n\t"
+      "add.cc.u32   %0, %0, l;\n\t"
+      "addc.cc.u32  %1, %1, h;\n\t"
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"      // carry ? 0xffffffff : 0
+      "add.cc.u32   %0, %0, c;\n\t"    // wrapped by 2^64: add 2^32 - 1 (cannot carry again)
+      "addc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return ((u64)r1 << 32) | r0;
+}
+
+__device__ __forceinline__ u64 sbox(u64 x) {
+  const u64 x2 = mul(x, x), x4 = mul(x2, x2), x3 = mul(x, x2);
+  return mul(x3, x4);
+}
+
+// al + 2^32 ah with al, ah < 2^42  ->  u64 representative
+__device__ __forceinline__ u64 reduce_split(u64 al, u64 ah) {
+  const u32 h0 = (u32)ah, h1 = (u32)(ah >> 32);  // value = al + h0 2^32 + h1 2^64
+  u64 t = al;
+  asm("mad.wide.u32 %0, %1, 0xffffffff, %0;" : "+l"(t) : "r"(h1));  // + h1 (2^32 - 1); < 2^43
+  u32 r0 = (u32)t, r1 = (u32)(t >> 32);
+  asm("{\n\t"
+      ".reg .u32 c;\n\t"
+      "add.cc.u32   %1, %1, %2;\n\t"
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"
+      "add.cc.u32   %0, %0, c;\n\t"    // wrapped by 2^64: add 2^32 - 1 (the wrapped value is < 2^43)
+      "addc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "+r"(r0), "+r"(r1)
+      : "r"(h0));
+  return ((u64)r1 << 32) | r0;
+}
+
+// s <- MDS s + (next round's constants); rc2 = 24 words of the split table
+__device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {
+  constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  u32 lo[12], hi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    lo[i] = (u32)s[i];
+    hi[i] = (u32)(s[i] >> 32);
+  }
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    u64 al = rc2[2 * r], ah = rc2[2 * r + 1];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const u32 c = (r == 0 && i == 0) ? C[0] + 8 : C[i];
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + r) % 12]), "r"(c));
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + r) % 12]), "r"(c));
+    }
+    s[r] = reduce_split(al, ah);
+  }
+}
+
+// The whole permutation is ONE loop over the 30 rounds with one copy of the S-box code (three lanes at a
+// time, lanes rotated through fixed registers) and one copy of the MDS code: ~1.7 k instructions, so it
+// stays inside the 32 KB L1.5 instruction cache. (Straight-line code per round type was 12.6 k
+// instructions and ran at a 51 % instruction-cache hit rate - ncu, profiles/r1_*.)
+__device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {  // inputs are canonical: s + k wraps at most once
+    const u64 k = rc2[2 * i] | (rc2[2 * i + 1] << 32);
+    u64 t = s[i] + k;
+    if (t < k) t += gl::EPS;
+    s[i] = t;
+  }
+#pragma unroll 1
+  for (int r = 0; r < N_ROUNDS; r++) {
+    if (r < HALF_FULL || r >= HALF_FULL + N_PARTIAL) {
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) {
+        const u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]);
+#pragma unroll
+        for (int i = 0; i < 9; i++) s[i] = s[i + 3];
+        s[9] = t0;
+        s[10] = t1;
+        s[11] = t2;
+      }
+    } else {
+      s[0] = sbox(s[0]);
+    }
+    mds_rc(s, rc2 + (r + 1) * 24);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = s[i] >= gl::P ? s[i] - gl::P : s[i];
+}
+
+}  // namespace lazy
+#endif
+
+PB_HD void permute(u64 s[12]) {
+#if defined(__CUDA_ARCH__)
+  lazy::permute(s, RC2_DEV);
+#else
+  permute_generic(s);
+#endif
 }
 
 struct Digest {

@@ -1,0 +1,192 @@
+// Micro-benchmark (GPU): Poseidon permutation variants and integer pipe rates. Build: see Makefile.
+#include "../../plonky2_bn254_b200/csrc/compat.cuh"
+namespace lazy {
+static constexpr u64 EPS = 0xFFFFFFFFULL, P = 0xFFFFFFFF00000001ULL;
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0, x1, x2, x3, m, l, h, c;\n\t"
+      "mul.lo.u32     x0, %2, %4;\n\t"
+      "mul.hi.u32     x1, %2, %4;\n\t"
+      "mad.lo.cc.u32  x1, %2, %5, x1;\n\t"
+      "madc.hi.u32    x2, %2, %5, 0;\n\t"
+      "mad.lo.cc.u32  x1, %3, %4, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+      "addc.u32       x3, 0, 0;\n\t"
+      "mad.lo.cc.u32  x2, %3, %5, x2;\n\t"
+      "madc.hi.u32    x3, %3, %5, x3;\n\t"
+      "sub.cc.u32   %0, x0, x3;\n\t"
+      "subc.cc.u32  %1, x1, 0;\n\t"
+      "subc.u32     m, 0, 0;\n\t"
+      "sub.cc.u32   %0, %0, m;\n\t"
+      "subc.u32     %1, %1, 0;\n\t"
+      "sub.cc.u32   l, 0, x2;\n\t"
+      "subc.u32     h, x2, 0;\n\t"
+      "add.cc.u32   %0, %0, l;\n\t"
+      "addc.cc.u32  %1, %1, h;\n\t"
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"
+      "add.cc.u32   %0, %0, c;\n\t"
+      "addc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return ((u64)r1 << 32) | r0;
+}
+__device__ __forceinline__ u64 sbox(u64 x) {
+  const u64 x2 = mul(x, x), x4 = mul(x2, x2), x3 = mul(x, x2);
+  return mul(x3, x4);
+}
+__device__ __forceinline__ u64 reduce_split(u64 al, u64 ah) {
+  const u32 h0 = (u32)ah, h1 = (u32)(ah >> 32);
+  u64 t = al;
+  asm("mad.wide.u32 %0, %1, 0xffffffff, %0;" : "+l"(t) : "r"(h1));
+  u32 r0 = (u32)t, r1 = (u32)(t >> 32);
+  asm("{\n\t"
+      ".reg .u32 c;\n\t"
+      "add.cc.u32   %1, %1, %2;\n\t"
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"
+      "add.cc.u32   %0, %0, c;\n\t"
+      "addc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "+r"(r0), "+r"(r1)
+      : "r"(h0));
+  return ((u64)r1 << 32) | r0;
+}
+// rc2: [12][2] u64 = (lo half, hi half) of the next round's constants
+__device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {
+  constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  u32 lo[12], hi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { lo[i] = (u32)s[i]; hi[i] = (u32)(s[i] >> 32); }
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    u64 al = rc2[2 * r], ah = rc2[2 * r + 1];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const u32 c = (r == 0 && i == 0) ? C[0] + 8 : C[i];
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + r) % 12]), "r"(c));
+      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + r) % 12]), "r"(c));
+    }
+    s[r] = reduce_split(al, ah);
+  }
+}
+__device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
+  // rc2[0] block holds round 0's constants: s += rc (canonical inputs)
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    u64 k = rc2[2 * i] | (rc2[2 * i + 1] << 32);
+    u64 t = s[i] + k;
+    if (t < k) t += EPS;
+    s[i] = t;
+  }
+#pragma unroll 1
+  for (int r = 0; r < 30; r++) {
+    if (r < 4 || r >= 26) {
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) {
+        const u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]);
+#pragma unroll
+        for (int i = 0; i < 9; i++) s[i] = s[i + 3];
+        s[9] = t0; s[10] = t1; s[11] = t2;
+      }
+    } else {
+      s[0] = sbox(s[0]);
+    }
+    mds_rc(s, rc2 + (r + 1) * 24);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = s[i] >= P ? s[i] - P : s[i];
+}
+}
+
+#include "../../plonky2_bn254_b200/csrc/poseidon.cuh"
+#include <cstdio>
+#include <vector>
+#include <cuda_runtime.h>
+
+__global__ void __launch_bounds__(128) k_compact(const u64* in, u64* out, const u64* rc2g, int reps) {
+  __shared__ u64 rc2[31 * 24];
+  for (int i = threadIdx.x; i < 31 * 24; i += blockDim.x) rc2[i] = rc2g[i];
+  __syncthreads();
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  u64 s[12];
+  for (int k = 0; k < 12; k++) s[k] = in[i * 12 + k];
+  for (int r = 0; r < reps; r++) lazy::permute(s, rc2);
+  for (int k = 0; k < 12; k++) out[i * 12 + k] = s[k];
+}
+__global__ void __launch_bounds__(128) k_generic(const u64* in, u64* out, int reps) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  u64 s[12];
+  for (int k = 0; k < 12; k++) s[k] = in[i * 12 + k];
+  for (int r = 0; r < reps; r++) poseidon::permute_generic(s);
+  for (int k = 0; k < 12; k++) out[i * 12 + k] = s[k];
+}
+// pipe-rate probes: N independent chains per thread
+template <int MODE>
+__global__ void k_rate(u32* out, int iters) {
+  u32 a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7;
+  u64 acc[8];
+  for (int j = 0; j < 8; j++) acc[j] = a + j;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (MODE == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+      if (MODE == 1) { u32 lo = (u32)acc[j]; asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b)); acc[j] = lo; }
+      if (MODE == 2) { u32 lo = (u32)acc[j]; asm volatile("add.u32 %0, %0, %1;" : "+r"(lo) : "r"(b)); acc[j] = lo; }
+      if (MODE == 3) { u64 t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"((u32)acc[j]), "r"(b)); acc[j] = t; }
+    }
+  }
+  u64 x = 0;
+  for (int j = 0; j < 8; j++) x ^= acc[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (u32)x ^ (u32)(x >> 32);
+}
+
+static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+int main() {
+  const size_t n = (size_t)148 * 8 * 128 * 8;  // states
+  const int reps = 16;
+  std::vector<u64> h(n * 12);
+  u64 x = 88172645463325252ULL;
+  for (auto& v : h) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = x % 0xFFFFFFFF00000001ULL; }
+  for (int k = 0; k < 12; k++) { h[k] = 0; h[12 + k] = k; h[24 + k] = 0xFFFFFFFF00000000ULL; }
+  std::vector<u64> rc2(31 * 24, 0);
+  for (int i = 0; i < 360; i++) { rc2[2 * i] = poseidon::RC_HOST[i] & 0xFFFFFFFFULL; rc2[2 * i + 1] = poseidon::RC_HOST[i] >> 32; }
+  u64 *din, *dout, *dout2, *drc;
+  cudaMalloc(&din, n * 96); cudaMalloc(&dout, n * 96); cudaMalloc(&dout2, n * 96); cudaMalloc(&drc, rc2.size() * 8);
+  cudaMemcpy(din, h.data(), n * 96, cudaMemcpyHostToDevice);
+  cudaMemcpy(drc, rc2.data(), rc2.size() * 8, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  // correctness: one permutation each
+  k_generic<<<n / 128, 128>>>(din, dout, 1);
+  k_compact<<<n / 128, 128>>>(din, dout2, drc, 1);
+  std::vector<u64> a(n * 12), b(n * 12);
+  cudaMemcpy(a.data(), dout, n * 96, cudaMemcpyDeviceToHost);
+  cudaMemcpy(b.data(), dout2, n * 96, cudaMemcpyDeviceToHost);
+  size_t bad = 0; for (size_t i = 0; i < n * 12; i++) bad += a[i] != b[i];
+  printf("KAT0 %016llx (want 3c18a9786cb0b359)  KAT1 %016llx (want d64e1e3efc5b8e9e)  mismatches generic vs compact: %zu  err=%s\n",
+         (unsigned long long)a[0], (unsigned long long)a[12], bad, cudaGetErrorString(cudaGetLastError()));
+  for (int pass = 0; pass < 2; pass++) {
+    cudaEventRecord(e0); k_generic<<<n / 128, 128>>>(din, dout, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float tg = time_ms(e0, e1);
+    cudaEventRecord(e0); k_compact<<<n / 128, 128>>>(din, dout2, drc, reps); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float tc = time_ms(e0, e1);
+    printf("generic %.3f ms = %.3f Gperm/s   compact %.3f ms = %.3f Gperm/s\n", tg, n * reps / tg * 1e-6, tc, n * reps / tc * 1e-6);
+  }
+  u32* dr; cudaMalloc(&dr, 148 * 16 * 256 * 4);
+  const int iters = 4096;
+  const double ops = 148.0 * 16 * 256 * iters * 8;
+  float t[4];
+  for (int pass = 0; pass < 2; pass++) {
+    cudaEventRecord(e0); k_rate<0><<<148 * 16, 256>>>(dr, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); t[0] = time_ms(e0, e1);
+    cudaEventRecord(e0); k_rate<1><<<148 * 16, 256>>>(dr, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); t[1] = time_ms(e0, e1);
+    cudaEventRecord(e0); k_rate<2><<<148 * 16, 256>>>(dr, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); t[2] = time_ms(e0, e1);
+    cudaEventRecord(e0); k_rate<3><<<148 * 16, 256>>>(dr, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); t[3] = time_ms(e0, e1);
+  }
+  const char* names[4] = {"mad.wide.u32 (acc chain)", "mad.lo.u32", "add.u32", "mul.wide.u32"};
+  for (int m = 0; m < 4; m++) printf("%-26s %.3f ms  %.2f Tops/s  %.1f lanes/clk/SM @1.965GHz\n", names[m], t[m], ops / t[m] * 1e-9, ops / t[m] * 1e3 / 148 / 1.965e9);
+  return 0;
+}
