@@ -762,6 +762,43 @@ struct HistK {  // one thread per used row: frequency[v] += 1 for every range-ch
     }
   }
 };
+#if !PB_HOSTSIM
+// K2 on the device: the 2^16-bin histogram lives in shared memory, half of the bins per CTA (32768 x u32 =
+// 128 KB), so the (rc_hi - rc_lo) x used cells cost shared-memory atomics instead of global ones; every CTA
+// of a half streams its row range of all range-checked columns (coalesced 8-byte loads, the matrix is read
+// twice in total) and flushes its non-zero bins with one global atomic each. Zero cells - by far the most
+// frequent value - are counted with a warp ballot.
+__global__ void __launch_bounds__(1024) k_range_hist(const u64* __restrict__ trace, u64* __restrict__ freq, size_t n_rows,
+                                                     size_t used, int rc_lo, int rc_hi, int* err) {
+  extern __shared__ u32 hist[];
+  const u32 half = blockIdx.y;
+  for (int i = threadIdx.x; i < 32768; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const size_t per = ((used + gridDim.x - 1) / gridDim.x + 1023) & ~(size_t)1023;
+  const size_t r0 = (size_t)blockIdx.x * per, r1 = r0 + per < used ? r0 + per : used;  // used is a multiple of 512
+  const u32 lane = threadIdx.x & 31;
+  bool bad = false;
+  for (int c = rc_lo; c < rc_hi; c++) {
+    const u64* col = trace + (size_t)c * n_rows;
+    for (size_t base = r0 + (threadIdx.x & ~31u); base < r1; base += blockDim.x) {  // whole warps: 32 | r1
+      const u64 v = col[base + lane];
+      bad |= v >= 65536;
+      const u32 zeros = __ballot_sync(0xffffffffu, v == 0);
+      if (v == 0) {
+        if (half == 0 && lane == (u32)(__ffs(zeros) - 1)) atomicAdd(&hist[0], (u32)__popc(zeros));
+      } else if ((u32)(v >> 15) == half) {
+        atomicAdd(&hist[(u32)v & 32767u], 1u);
+      }
+    }
+  }
+  if (bad) set_err(err, ERR_INTERNAL);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32768; i += blockDim.x) {
+    const u32 h = hist[i];
+    if (h) atomicAdd((unsigned long long*)(freq + half * 32768u + i), (unsigned long long)h);
+  }
+}
+#endif
 struct AddK {
   u64* p;
   u64 v;
@@ -815,7 +852,22 @@ void generate(Arena& ar, int kind, const u64* d_inputs, const u64* d_ts, size_t 
   }
   pb_launch("range counter", RangeCounterK{d_trace + (size_t)l.range_counter * n_rows}, n_rows, s);
   u64* freq = d_trace + (size_t)l.freq * n_rows;
+#if PB_HOSTSIM
   if (used > 0) pb_launch("range histogram", HistK{d_trace, freq, n_rows, l.rc_lo, l.rc_hi, d_err}, used, s, 128);
+#else
+  if (used > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PB_CUDA(cudaFuncSetAttribute(k_range_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+      attr_set = true;
+    }
+    size_t bx = (used + 1023) / 1024;
+    if (bx > 74) bx = 74;  // 2 halves x 74 = one CTA per SM
+    k_range_hist<<<dim3((unsigned)bx, 2), 1024, 32768 * 4, s>>>(d_trace, freq, n_rows, used, l.rc_lo, l.rc_hi, d_err);
+    g_pb_launches++;
+    pb_check_last("range histogram");
+  }
+#endif
   if (used < n_rows) {
     // padding rows are all zero: (rc_hi - rc_lo) look-ups of the value 0 each
     u64 extra = (u64)(n_rows - used) * (u64)(l.rc_hi - l.rc_lo);

@@ -107,7 +107,10 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
 #include <vector>
 #include <cuda_runtime.h>
 
-__global__ void __launch_bounds__(128) k_compact(const u64* in, u64* out, const u64* rc2g, int reps) {
+#ifndef MINB
+#define MINB 1
+#endif
+__global__ void __launch_bounds__(128, MINB) k_compact(const u64* in, u64* out, const u64* rc2g, int reps) {
   __shared__ u64 rc2[31 * 24];
   for (int i = threadIdx.x; i < 31 * 24; i += blockDim.x) rc2[i] = rc2g[i];
   __syncthreads();
