@@ -14,9 +14,10 @@
 //   - lanes live as arbitrary u64 representatives of their residue (no conditional subtractions);
 //   - a field multiplication is 4 IMAD.WIDE.U32 plus a carry-chain reduction written in PTX
 //     (2^64 = 2^32 - 1, 2^96 = -1 mod p): add.cc / addc, no compare-and-select;
-//   - the MDS layer uses that all matrix entries are < 2^6: lanes are split into 32-bit halves and the
-//     two half-sums (< 2^42) are each 12 IMAD.WIDE.U32 accumulations; the next round's constants are
-//     folded into the accumulators' initial values, so "add round constants" costs nothing;
+//   - the MDS layer uses that all matrix entries are < 2^6: lanes are cut into 16-bit pieces and two
+//     (piece x entry) products are accumulated per dp2a instruction (IDP.2A, 288 per layer); with
+//     IMAD.WIDE on 32-bit halves ptxas emits one IMAD.WIDE plus one 64-bit carry-chain addition per
+//     product, and those IADD3/IADD3.X were 60 % of all stall samples (profiles/r1_poseidon_compact.txt);
 //   - the optimised-partial-round factorisation of the reference implementation is NOT used: with
 //     6-bit matrix entries the dense layer (288 IMAD.WIDE) is as cheap on this machine as the sparse
 //     layer with 64-bit constants (22 full multiplications) - see DESIGN.md.
@@ -123,41 +124,44 @@ static __constant__ u64 RC2_DEV[RC2_WORDS] = {
 namespace lazy {
 
 // a * b mod p for arbitrary u64 representatives; result is an arbitrary u64 representative.
-// product words (x3 x2 x1 x0) by a mad.lo.cc / madc.hi.cc chain (ptxas: IMAD.WIDE.U32 with carry-out),
-// then  x0 + x1 2^32 + x2 2^64 + x3 2^96 == (x1:x0) - x3 + x2 (2^32 - 1)  (mod p).
+// Four full-rate IMAD.WIDE.U32 products (mul.hi / IMAD.HI and carry-out IMADs are half rate on B200,
+// tools/microbench/pipe_rates.cu) summed by carry chains into (x3 x2 x1 x0), then
+//   x0 + x1 2^32 + x2 2^64 + x3 2^96 == (x1:x0) - x3 + x2 (2^32 - 1)  (mod p).
 __device__ __forceinline__ u64 mul(u64 a, u64 b) {
   const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
   u32 r0, r1;
   asm("{\n\t"
       ".reg .u32 x0, x1, x2, x3, m, l, h, c;\n\t"
-      "mul.lo.u32     x0, %2, %4;\n\t"
-      "mul.hi.u32     x1, %2, %4;\n\t"
-      "mad.lo.cc.u32  x1, %2, %5, x1;\n\t"
-      "madc.hi.u32    x2, %2, %5, 0;\n\t"
-      "mad.lo.cc.u32  x1, %3, %4, x1;\n\t"
-      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
-      "addc.u32       x3, 0, 0;\n\t"
-      "mad.lo.cc.u32  x2, %3, %5, x2;\n\t"
-      "madc.hi.u32    x3, %3, %5, x3;\n\t"
-      "sub.cc.u32   %0, x0, x3;\n\t"   // (x1:x0) - x3
+      ".reg .u64 P, Q, R, S; .reg .u32 p1, q0, q1, s0, s1, t0, t1;\n\t"
+      "mul.wide.u32 P, %2, %4;\n\t"
+      "mul.wide.u32 Q, %2, %5;\n\t"
+      "mul.wide.u32 R, %3, %4;\n\t"
+      "mul.wide.u32 S, %3, %5;\n\t"
+      "mov.b64 {x0, p1}, P; mov.b64 {q0, q1}, Q; mov.b64 {t0, t1}, R; mov.b64 {s0, s1}, S;\n\t"
+      "add.cc.u32   x1, p1, q0;\n\t"
+      "addc.cc.u32  x2, q1, s0;\n\t"
+      "addc.u32     x3, s1, 0;\n\t"
+      "add.cc.u32   x1, x1, t0;\n\t"
+      "addc.cc.u32  x2, x2, t1;\n\t"
+      "addc.u32     x3, x3, 0;\n\t"
+      "sub.cc.u32   %0, x0, x3;\n\t"
       "subc.cc.u32  %1, x1, 0;\n\t"
-      "subc.u32     m, 0, 0;\n\t"      // borrow ? 0xffffffff : 0
-      "sub.cc.u32   %0, %0, m;\n\t"    // wrapped by 2^64: subtract 2^32 - 1 (cannot borrow again)
+      "subc.u32     m, 0, 0;\n\t"
+      "sub.cc.u32   %0, %0, m;\n\t"
       "subc.u32     %1, %1, 0;\n\t"
-      "sub.cc.u32   l, 0, x2;\n\t"     // x2 (2^32 - 1) = (x2 << 32) - x2
+      "sub.cc.u32   l, 0, x2;\n\t"
       "subc.u32     h, x2, 0;\n\t"
       "add.cc.u32   %0, %0, l;\n\t"
       "addc.cc.u32  %1, %1, h;\n\t"
       "addc.u32     c, 0, 0;\n\t"
-      "sub.u32      c, 0, c;\n\t"      // carry ? 0xffffffff : 0
-      "add.cc.u32   %0, %0, c;\n\t"    // wrapped by 2^64: add 2^32 - 1 (cannot carry again)
+      "sub.u32      c, 0, c;\n\t"
+      "add.cc.u32   %0, %0, c;\n\t"
       "addc.u32     %1, %1, 0;\n\t"
       "}"
       : "=&r"(r0), "=&r"(r1)
       : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return ((u64)r1 << 32) | r0;
 }
-
 __device__ __forceinline__ u64 sbox(u64 x) {
   const u64 x2 = mul(x, x), x4 = mul(x2, x2), x3 = mul(x, x2);
   return mul(x3, x4);
@@ -182,28 +186,47 @@ __device__ __forceinline__ u64 reduce_split(u64 al, u64 ah) {
   return ((u64)r1 << 32) | r0;
 }
 
-// s <- MDS s + (next round's constants); rc2 = 24 words of the split table
-__device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {
-  constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  u32 lo[12], hi[12];
+// s <- MDS s + (next round's constants); rc2 = 24 words of the split table.
+// MDS on 16-bit pieces with dp2a: lanes are cut into four 16-bit pieces; pieces of the same weight of two
+// neighbouring lanes are packed into one register, and one dp2a adds two (piece x 6-bit entry) products to
+// a 32-bit accumulator: 6 dp2a per (output lane, weight) instead of 12 IMAD.WIDE + 12 64-bit additions.
+template <int R, int K>
+struct Coef {
+  static constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  static constexpr u32 m(int r, int i) { return C[(i - r + 12) % 12] + ((r == 0 && i == 0) ? 8u : 0u); }
+  static constexpr u32 value = m(R, 2 * K) | (m(R, 2 * K + 1) << 8);
+};
+template <int R, int K>
+__device__ __forceinline__ void dp_row(u32 acc[4], const u32 (*X)[4]) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    lo[i] = (u32)s[i];
-    hi[i] = (u32)(s[i] >> 32);
-  }
-#pragma unroll
-  for (int r = 0; r < 12; r++) {
-    u64 al = rc2[2 * r], ah = rc2[2 * r + 1];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const u32 c = (r == 0 && i == 0) ? C[0] + 8 : C[i];
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + r) % 12]), "r"(c));
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + r) % 12]), "r"(c));
-    }
-    s[r] = reduce_split(al, ah);
-  }
+  for (int q = 0; q < 4; q++)
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(X[K][q]), "r"(Coef<R, K>::value));
+  if constexpr (K + 1 < 6) dp_row<R, K + 1>(acc, X);
 }
-
+template <int R>
+__device__ __forceinline__ void mds_rows(u64 s[12], const u32 (*X)[4], const u64* rc2) {
+  u32 acc[4] = {0, 0, 0, 0};
+  dp_row<R, 0>(acc, X);
+  u64 al = rc2[2 * R], ah = rc2[2 * R + 1];
+  asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(al) : "r"(acc[0]));
+  asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(al) : "r"(acc[1]));
+  asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(ah) : "r"(acc[2]));
+  asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(ah) : "r"(acc[3]));
+  s[R] = reduce_split(al, ah);
+  if constexpr (R + 1 < 12) mds_rows<R + 1>(s, X, rc2);
+}
+__device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {
+  u32 X[6][4];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const u32 a0 = (u32)s[2 * k], a1 = (u32)(s[2 * k] >> 32), b0 = (u32)s[2 * k + 1], b1 = (u32)(s[2 * k + 1] >> 32);
+    X[k][0] = __byte_perm(a0, b0, 0x5410);
+    X[k][1] = __byte_perm(a0, b0, 0x7632);
+    X[k][2] = __byte_perm(a1, b1, 0x5410);
+    X[k][3] = __byte_perm(a1, b1, 0x7632);
+  }
+  mds_rows<0>(s, X, rc2);
+}
 // The whole permutation is ONE loop over the 30 rounds with one copy of the S-box code (three lanes at a
 // time, lanes rotated through fixed registers) and one copy of the MDS code: ~1.7 k instructions, so it
 // stays inside the 32 KB L1.5 instruction cache. (Straight-line code per round type was 12.6 k

@@ -7,15 +7,18 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
   u32 r0, r1;
   asm("{\n\t"
       ".reg .u32 x0, x1, x2, x3, m, l, h, c;\n\t"
-      "mul.lo.u32     x0, %2, %4;\n\t"
-      "mul.hi.u32     x1, %2, %4;\n\t"
-      "mad.lo.cc.u32  x1, %2, %5, x1;\n\t"
-      "madc.hi.u32    x2, %2, %5, 0;\n\t"
-      "mad.lo.cc.u32  x1, %3, %4, x1;\n\t"
-      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
-      "addc.u32       x3, 0, 0;\n\t"
-      "mad.lo.cc.u32  x2, %3, %5, x2;\n\t"
-      "madc.hi.u32    x3, %3, %5, x3;\n\t"
+      ".reg .u64 P, Q, R, S; .reg .u32 p1, q0, q1, s0, s1, t0, t1;\n\t"
+      "mul.wide.u32 P, %2, %4;\n\t"
+      "mul.wide.u32 Q, %2, %5;\n\t"
+      "mul.wide.u32 R, %3, %4;\n\t"
+      "mul.wide.u32 S, %3, %5;\n\t"
+      "mov.b64 {x0, p1}, P; mov.b64 {q0, q1}, Q; mov.b64 {t0, t1}, R; mov.b64 {s0, s1}, S;\n\t"
+      "add.cc.u32   x1, p1, q0;\n\t"
+      "addc.cc.u32  x2, q1, s0;\n\t"
+      "addc.u32     x3, s1, 0;\n\t"
+      "add.cc.u32   x1, x1, t0;\n\t"
+      "addc.cc.u32  x2, x2, t1;\n\t"
+      "addc.u32     x3, x3, 0;\n\t"
       "sub.cc.u32   %0, x0, x3;\n\t"
       "subc.cc.u32  %1, x1, 0;\n\t"
       "subc.u32     m, 0, 0;\n\t"
@@ -56,22 +59,45 @@ __device__ __forceinline__ u64 reduce_split(u64 al, u64 ah) {
   return ((u64)r1 << 32) | r0;
 }
 // rc2: [12][2] u64 = (lo half, hi half) of the next round's constants
+// MDS on 16-bit pieces with dp2a: lanes are cut into four 16-bit pieces; pieces of the same weight of two
+// neighbouring lanes are packed into one register, and one dp2a adds two (piece x 6-bit entry) products to
+// a 32-bit accumulator: 6 dp2a per (output lane, weight) instead of 12 IMAD.WIDE + 12 64-bit additions.
+template <int R, int K>
+struct Coef {
+  static constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  static constexpr u32 m(int r, int i) { return C[(i - r + 12) % 12] + ((r == 0 && i == 0) ? 8u : 0u); }
+  static constexpr u32 value = m(R, 2 * K) | (m(R, 2 * K + 1) << 8);
+};
+template <int R, int K>
+__device__ __forceinline__ void dp_row(u32 acc[4], const u32 (*X)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(acc[q]) : "r"(X[K][q]), "r"(Coef<R, K>::value));
+  if constexpr (K + 1 < 6) dp_row<R, K + 1>(acc, X);
+}
+template <int R>
+__device__ __forceinline__ void mds_rows(u64 s[12], const u32 (*X)[4], const u64* rc2) {
+  u32 acc[4] = {0, 0, 0, 0};
+  dp_row<R, 0>(acc, X);
+  u64 al = rc2[2 * R], ah = rc2[2 * R + 1];
+  asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(al) : "r"(acc[0]));
+  asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(al) : "r"(acc[1]));
+  asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(ah) : "r"(acc[2]));
+  asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(ah) : "r"(acc[3]));
+  s[R] = reduce_split(al, ah);
+  if constexpr (R + 1 < 12) mds_rows<R + 1>(s, X, rc2);
+}
 __device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {
-  constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  u32 lo[12], hi[12];
+  u32 X[6][4];
 #pragma unroll
-  for (int i = 0; i < 12; i++) { lo[i] = (u32)s[i]; hi[i] = (u32)(s[i] >> 32); }
-#pragma unroll
-  for (int r = 0; r < 12; r++) {
-    u64 al = rc2[2 * r], ah = rc2[2 * r + 1];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const u32 c = (r == 0 && i == 0) ? C[0] + 8 : C[i];
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + r) % 12]), "r"(c));
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + r) % 12]), "r"(c));
-    }
-    s[r] = reduce_split(al, ah);
+  for (int k = 0; k < 6; k++) {
+    const u32 a0 = (u32)s[2 * k], a1 = (u32)(s[2 * k] >> 32), b0 = (u32)s[2 * k + 1], b1 = (u32)(s[2 * k + 1] >> 32);
+    X[k][0] = __byte_perm(a0, b0, 0x5410);
+    X[k][1] = __byte_perm(a0, b0, 0x7632);
+    X[k][2] = __byte_perm(a1, b1, 0x5410);
+    X[k][3] = __byte_perm(a1, b1, 0x7632);
   }
+  mds_rows<0>(s, X, rc2);
 }
 __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
   // rc2[0] block holds round 0's constants: s += rc (canonical inputs)
