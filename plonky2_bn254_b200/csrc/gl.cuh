@@ -51,11 +51,57 @@ PB_HD u64 reduce160(u64 lo, u64 hi, u64 c2) {
   u64 r = reduce128(lo, hi);
   return sub(r, reduce128(c2 << 32, 0));
 }
+#if defined(__CUDA_ARCH__)
+// Device forms. B200 integer pipes (tools/microbench/pipe_rates.cu): IMAD.WIDE.U32 runs at full FMA-pipe
+// rate, mul.hi / IMAD.HI and carry-out IMADs at half rate, and compare-and-select sequences cost two ALU
+// slots per 32-bit word - so products are four mul.wide.u32 and all carries are add.cc / addc chains.
+// a * b for ANY u64 a, b; the result is some u64 congruent to a * b mod p (not necessarily < p).
+__device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0, x1, x2, x3, m, l, h, c;\n\t"
+      ".reg .u64 P, Q, R, S; .reg .u32 p1, q0, q1, s0, s1, t0, t1;\n\t"
+      "mul.wide.u32 P, %2, %4;\n\t"
+      "mul.wide.u32 Q, %2, %5;\n\t"
+      "mul.wide.u32 R, %3, %4;\n\t"
+      "mul.wide.u32 S, %3, %5;\n\t"
+      "mov.b64 {x0, p1}, P; mov.b64 {q0, q1}, Q; mov.b64 {t0, t1}, R; mov.b64 {s0, s1}, S;\n\t"
+      "add.cc.u32   x1, p1, q0;\n\t"
+      "addc.cc.u32  x2, q1, s0;\n\t"
+      "addc.u32     x3, s1, 0;\n\t"
+      "add.cc.u32   x1, x1, t0;\n\t"
+      "addc.cc.u32  x2, x2, t1;\n\t"
+      "addc.u32     x3, x3, 0;\n\t"
+      "sub.cc.u32   %0, x0, x3;\n\t"   // (x1:x0) - x3              (2^96 == -1)
+      "subc.cc.u32  %1, x1, 0;\n\t"
+      "subc.u32     m, 0, 0;\n\t"      // borrow ? 0xffffffff : 0
+      "sub.cc.u32   %0, %0, m;\n\t"    // wrapped by 2^64: subtract 2^32 - 1 (cannot borrow again)
+      "subc.u32     %1, %1, 0;\n\t"
+      "sub.cc.u32   l, 0, x2;\n\t"     // x2 (2^32 - 1) = (x2 << 32) - x2   (2^64 == 2^32 - 1)
+      "subc.u32     h, x2, 0;\n\t"
+      "add.cc.u32   %0, %0, l;\n\t"
+      "addc.cc.u32  %1, %1, h;\n\t"
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"      // carry ? 0xffffffff : 0
+      "add.cc.u32   %0, %0, c;\n\t"    // wrapped by 2^64: add 2^32 - 1 (cannot carry again)
+      "addc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return ((u64)r1 << 32) | r0;
+}
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+  const u64 r = mul_lazy(a, b);
+  return r >= P ? r - P : r;
+}
+#else
 PB_HD u64 mul(u64 a, u64 b) {
   u64 lo, hi;
   mul_wide(a, b, lo, hi);
   return reduce128(lo, hi);
 }
+#endif
 PB_HD u64 sqr(u64 a) { return mul(a, a); }
 PB_HD u64 pow(u64 a, u64 e) {
   u64 r = 1;
@@ -80,6 +126,48 @@ PB_HD u64 inv(u64 a) {
 }
 
 // lazy accumulator for sums of products: 64x64 -> 128-bit terms accumulated in 160 bits
+#if defined(__CUDA_ARCH__)
+struct Acc {
+  u32 w0, w1, w2, w3, w4;
+  __device__ __forceinline__ Acc() : w0(0), w1(0), w2(0), w3(0), w4(0) {}
+  // acc += a * b (any u64 a, b): 4 mul.wide.u32 + 13 carry-chain additions
+  __device__ __forceinline__ void mac(u64 a, u64 b) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("{\n\t"
+        ".reg .u64 P, Q, R, S; .reg .u32 p0, p1, q0, q1, r0, r1, s0, s1;\n\t"
+        "mul.wide.u32 P, %5, %7;\n\t"
+        "mul.wide.u32 Q, %5, %8;\n\t"
+        "mul.wide.u32 R, %6, %7;\n\t"
+        "mul.wide.u32 S, %6, %8;\n\t"
+        "mov.b64 {p0, p1}, P; mov.b64 {q0, q1}, Q; mov.b64 {r0, r1}, R; mov.b64 {s0, s1}, S;\n\t"
+        "add.cc.u32   %0, %0, p0;\n\t"
+        "addc.cc.u32  %1, %1, p1;\n\t"
+        "addc.cc.u32  %2, %2, s0;\n\t"
+        "addc.cc.u32  %3, %3, s1;\n\t"
+        "addc.u32     %4, %4, 0;\n\t"
+        "add.cc.u32   %1, %1, q0;\n\t"
+        "addc.cc.u32  %2, %2, q1;\n\t"
+        "addc.cc.u32  %3, %3, 0;\n\t"
+        "addc.u32     %4, %4, 0;\n\t"
+        "add.cc.u32   %1, %1, r0;\n\t"
+        "addc.cc.u32  %2, %2, r1;\n\t"
+        "addc.cc.u32  %3, %3, 0;\n\t"
+        "addc.u32     %4, %4, 0;\n\t"
+        "}"
+        : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3), "+r"(w4)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  }
+  __device__ __forceinline__ void addv(u64 v) {
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, %4, 0;"
+        : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3), "+r"(w4)
+        : "r"((u32)v), "r"((u32)(v >> 32)));
+  }
+  __device__ __forceinline__ u64 reduce() const {
+    return reduce160(((u64)w1 << 32) | w0, ((u64)w3 << 32) | w2, w4);
+  }
+};
+#else
 struct Acc {
   u64 lo, hi;
   u32 c;
@@ -102,6 +190,7 @@ struct Acc {
   }
   PB_HD u64 reduce() const { return reduce160(lo, hi, c); }
 };
+#endif
 
 // ---- quadratic extension ---------------------------------------------------------------
 struct E2 {
