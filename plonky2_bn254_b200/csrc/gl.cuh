@@ -51,7 +51,7 @@ PB_HD u64 reduce160(u64 lo, u64 hi, u64 c2) {
   u64 r = reduce128(lo, hi);
   return sub(r, reduce128(c2 << 32, 0));
 }
-#if defined(__CUDA_ARCH__)
+#if !PB_HOSTSIM
 // Device forms. B200 integer pipes (tools/microbench/pipe_rates.cu): IMAD.WIDE.U32 runs at full FMA-pipe
 // rate, mul.hi / IMAD.HI and carry-out IMADs at half rate, and compare-and-select sequences cost two ALU
 // slots per 32-bit word - so products are four mul.wide.u32 and all carries are add.cc / addc chains.
@@ -91,17 +91,56 @@ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
       : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return ((u64)r1 << 32) | r0;
 }
-__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+// a + b and a - b for ANY u64 a, b; results are arbitrary u64 representatives. A wrap by 2^64 is
+// corrected by +-(2^32 - 1); the correction itself can wrap once more, never a third time.
+__device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 c;\n\t"
+      "add.cc.u32   %0, %2, %4;\n\t"
+      "addc.cc.u32  %1, %3, %5;\n\t"
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"
+      "add.cc.u32   %0, %0, c;\n\t"
+      "addc.cc.u32  %1, %1, 0;\n\t"
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"
+      "add.cc.u32   %0, %0, c;\n\t"
+      "addc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  return ((u64)r1 << 32) | r0;
+}
+__device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) {
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 m;\n\t"
+      "sub.cc.u32   %0, %2, %4;\n\t"
+      "subc.cc.u32  %1, %3, %5;\n\t"
+      "subc.u32     m, 0, 0;\n\t"    // borrow ? 0xffffffff : 0
+      "sub.cc.u32   %0, %0, m;\n\t"
+      "subc.cc.u32  %1, %1, 0;\n\t"
+      "subc.u32     m, 0, 0;\n\t"
+      "sub.cc.u32   %0, %0, m;\n\t"
+      "subc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+  return ((u64)r1 << 32) | r0;
+}
+__device__ __forceinline__ u64 canonical(u64 a) { return a >= P ? a - P : a; }
+#endif
+PB_HD u64 mul(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
   const u64 r = mul_lazy(a, b);
   return r >= P ? r - P : r;
-}
 #else
-PB_HD u64 mul(u64 a, u64 b) {
   u64 lo, hi;
   mul_wide(a, b, lo, hi);
   return reduce128(lo, hi);
-}
 #endif
+}
 PB_HD u64 sqr(u64 a) { return mul(a, a); }
 PB_HD u64 pow(u64 a, u64 e) {
   u64 r = 1;
@@ -126,12 +165,13 @@ PB_HD u64 inv(u64 a) {
 }
 
 // lazy accumulator for sums of products: 64x64 -> 128-bit terms accumulated in 160 bits
-#if defined(__CUDA_ARCH__)
+#if !PB_HOSTSIM
 struct Acc {
   u32 w0, w1, w2, w3, w4;
-  __device__ __forceinline__ Acc() : w0(0), w1(0), w2(0), w3(0), w4(0) {}
+  PB_HD Acc() : w0(0), w1(0), w2(0), w3(0), w4(0) {}
   // acc += a * b (any u64 a, b): 4 mul.wide.u32 + 13 carry-chain additions
-  __device__ __forceinline__ void mac(u64 a, u64 b) {
+  PB_HD void mac(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
     const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
     asm("{\n\t"
         ".reg .u64 P, Q, R, S; .reg .u32 p0, p1, q0, q1, r0, r1, s0, s1;\n\t"
@@ -156,14 +196,36 @@ struct Acc {
         "}"
         : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3), "+r"(w4)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+#else
+    u64 l, h;
+    mul_wide(a, b, l, h);
+    add3(l, h);
+#endif
   }
-  __device__ __forceinline__ void addv(u64 v) {
+  PB_HD void add3(u64 l, u64 h) {  // host pass only (never on a hot path)
+    u64 lo = ((u64)w1 << 32) | w0, hi = ((u64)w3 << 32) | w2;
+    lo += l;
+    u64 cy = lo < l;
+    hi += cy;
+    w4 += (hi < cy);
+    hi += h;
+    w4 += (hi < h);
+    w0 = (u32)lo;
+    w1 = (u32)(lo >> 32);
+    w2 = (u32)hi;
+    w3 = (u32)(hi >> 32);
+  }
+  PB_HD void addv(u64 v) {
+#if defined(__CUDA_ARCH__)
     asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, 0;\n\t"
         "addc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, %4, 0;"
         : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3), "+r"(w4)
         : "r"((u32)v), "r"((u32)(v >> 32)));
+#else
+    add3(v, 0);
+#endif
   }
-  __device__ __forceinline__ u64 reduce() const {
+  PB_HD u64 reduce() const {
     return reduce160(((u64)w1 << 32) | w0, ((u64)w3 << 32) | w2, w4);
   }
 };

@@ -36,40 +36,109 @@ static inline Plan make_plan(int L, int r) {
 
 #if !PB_HOSTSIM
 // ---------------------------------------------------------------------------------------------
+// Shared-memory tiles hold [row][column] with 2^LOGTC columns; one work item is a radix-Q butterfly
+// (Q = 8, 4 or 2: three, two or one radix-2 stages) on Q rows of one column, done in registers with
+// lazy u64 representatives (gl::mul_lazy / add_lazy / sub_lazy), so a 2^K-row transform costs
+// ceil(K / 3) shared-memory round trips and barriers instead of K. Logical word i lives at
+// i + (i >> 4): one pad word per 16 breaks the power-of-two strides of the last rounds (the Q rows of
+// an item are then adjacent), which would otherwise be 16-way bank conflicts.
+// Twiddles of order 2^k, k <= 13, come straight from the power tables: fwd_hi[e << (13 - k)].
+#define NTT_PHYS(i) ((i) + ((i) >> 4))
+
+template <int Q, bool DIF, int LOGTC>
+__device__ __forceinline__ void tile_round(u64* __restrict__ sm, const u64* __restrict__ tw, int K, int s, int tid, int nt) {
+  constexpr int LQ = Q == 8 ? 3 : Q == 4 ? 2 : 1;
+  const int items = ((1 << K) >> LQ) << LOGTC;
+  for (int t = tid; t < items; t += nt) {
+    const int c = t & ((1 << LOGTC) - 1), u = t >> LOGTC;
+    int base, step, j;
+    if (DIF) {
+      const int lstep = K - s - LQ;  // span = 2^(K - s) rows, the item's rows are span / Q apart
+      step = 1 << lstep;
+      j = u & (step - 1);
+      base = ((u >> lstep) << (K - s)) + j;
+    } else {
+      step = 1 << s;
+      j = u & (step - 1);
+      base = ((u >> s) << (s + LQ)) + j;
+    }
+    u64 x[Q];
+#pragma unroll
+    for (int m = 0; m < Q; m++) x[m] = sm[NTT_PHYS(((base + m * step) << LOGTC) + c)];
+#pragma unroll
+    for (int k = 0; k < LQ; k++) {
+      const int hb = DIF ? (Q >> (k + 1)) : (1 << k);
+#pragma unroll
+      for (int m = 0; m < Q; m++) {
+        if (m & hb) continue;
+        const int pos = m & (hb - 1);
+        const u64 a = x[m], b2 = x[m + hb];
+        if (DIF) {
+          const u64 w = tw[(j + pos * step) << (s + k)];
+          x[m] = gl::add_lazy(a, b2);
+          x[m + hb] = gl::mul_lazy(gl::sub_lazy(a, b2), w);
+        } else {
+          const u64 w = tw[(j + pos * step) << (K - 1 - (s + k))];
+          const u64 y = gl::mul_lazy(b2, w);
+          x[m] = gl::add_lazy(a, y);
+          x[m + hb] = gl::sub_lazy(a, y);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < Q; m++) sm[NTT_PHYS(((base + m * step) << LOGTC) + c)] = x[m];
+  }
+}
+
+// stages [s0, s1) of a 2^K-row transform on the tile, a barrier after every round
+template <bool DIF, int LOGTC>
+__device__ __forceinline__ void tile_stages(u64* sm, const u64* tw, int K, int s0, int s1, int tid, int nt) {
+  int s = s0;
+  while (s1 - s >= 3) {
+    tile_round<8, DIF, LOGTC>(sm, tw, K, s, tid, nt);
+    __syncthreads();
+    s += 3;
+  }
+  if (s1 - s == 2) {
+    tile_round<4, DIF, LOGTC>(sm, tw, K, s, tid, nt);
+    __syncthreads();
+  } else if (s1 - s == 1) {
+    tile_round<2, DIF, LOGTC>(sm, tw, K, s, tid, nt);
+    __syncthreads();
+  }
+}
+
+static constexpr int LOG_TC = 3;  // TC = 8
+static_assert((1 << LOG_TC) == TC, "tile width");
+static inline size_t tile_smem_words(int K1) {
+  size_t w = (size_t)(1 << K1) * TC;
+  return w + (w >> 4) + 16 + (1 << K1) / 2;
+}
+
 // pass A: inverse DIF over the top K1 index bits; rows r = 0..2^K1-1 at stride C = 2^(L-K1).
-static __global__ void __launch_bounds__(256) k_ntt_pass_a(const u64* __restrict__ in, u64* __restrict__ out, int L, int K1,
+static __global__ void __launch_bounds__(512) k_ntt_pass_a(const u64* __restrict__ in, u64* __restrict__ out, int L, int K1,
                                                     size_t in_stride, size_t out_stride, Tables t) {
   extern __shared__ u64 sm[];
   const int R = 1 << K1;
   const size_t C = (size_t)1 << (L - K1);
-  u64* tw = sm + (size_t)R * TC;  // R/2 inverse twiddles of order R
+  u64* tw = sm + NTT_PHYS(R * TC) + 16;  // R/2 inverse twiddles of order R
   const int tid = threadIdx.x, nt = blockDim.x;
   const size_t c0 = (size_t)blockIdx.x * TC;
   const u64* src = in + (size_t)blockIdx.y * in_stride;
   u64* dst = out + (size_t)blockIdx.y * out_stride;
-  for (int e = tid; e < R / 2; e += nt) tw[e] = tpow(t.inv_lo, t.inv_hi, (u64)e << (LOG_M - K1));
+  for (int e = tid; e < R / 2; e += nt) tw[e] = t.inv_hi[(size_t)e << (LOG_T - K1)];
   for (int idx = tid; idx < R * TC; idx += nt) {
-    int rr = idx / TC, c = idx % TC;
-    sm[idx] = src[(size_t)rr * C + c0 + c];
+    int rr = idx >> LOG_TC, c = idx & (TC - 1);
+    sm[NTT_PHYS(idx)] = src[(size_t)rr * C + c0 + c];
   }
   __syncthreads();
-  for (int s = 0; s < K1; s++) {
-    const int half = R >> (s + 1);
-    for (int b = tid; b < (R / 2) * TC; b += nt) {
-      int c = b % TC, p = b / TC;
-      int j = p & (half - 1), grp = p / half;
-      int i0 = (grp * 2 * half + j) * TC + c, i1 = i0 + half * TC;
-      u64 a = sm[i0], bb = sm[i1];
-      sm[i0] = gl::add(a, bb);
-      sm[i1] = gl::mul(gl::sub(a, bb), tw[j << s]);
-    }
-    __syncthreads();
-  }
+  tile_stages<true, LOG_TC>(sm, tw, K1, 0, K1, tid, nt);
   for (int idx = tid; idx < R * TC; idx += nt) {
-    int rr = idx / TC, c = idx % TC;
+    int rr = idx >> LOG_TC, c = idx & (TC - 1);
     u64 k1 = gl::brev32((u32)rr, K1);
     u64 e = (c0 + c) * k1;  // < 2^L
-    dst[(size_t)rr * C + c0 + c] = gl::mul(sm[idx], tpow(t.inv_lo, t.inv_hi, e << (LOG_M - L)));
+    // intermediate buffer: any u64 representative is fine for the next kernel
+    dst[(size_t)rr * C + c0 + c] = gl::mul_lazy(sm[NTT_PHYS(idx)], tpow(t.inv_lo, t.inv_hi, e << (LOG_M - L)));
   }
 }
 
@@ -79,46 +148,34 @@ static __global__ void __launch_bounds__(256) k_ntt_fused(const u64* __restrict_
                                                    int mode) {
   extern __shared__ u64 sm[];
   const int C = 1 << Kc, Cp = C << r, K1 = L - Kc;
-  u64* small = sm;                 // C
-  u64* big = sm + C;               // Cp
-  u64* twf = big + Cp;             // Cp/2 forward twiddles of order Cp
-  u64* twi = twf + Cp / 2;         // C/2 inverse twiddles of order C
+  u64* small = sm;                              // C (padded)
+  u64* big = small + NTT_PHYS(C) + 16;          // Cp (padded)
+  u64* twf = big + NTT_PHYS(Cp) + 16;           // Cp/2 forward twiddles of order Cp
+  u64* twi = twf + Cp / 2;                      // C/2 inverse twiddles of order C
   const int tid = threadIdx.x, nt = blockDim.x;
   const size_t blk = blockIdx.x;
   const u64* src = in + (size_t)blockIdx.y * in_stride;
   u64* dst = out + (size_t)blockIdx.y * out_stride;
   if (mode != FROM_COEFFS_LDE)
-    for (int e = tid; e < C / 2; e += nt) twi[e] = tpow(t.inv_lo, t.inv_hi, (u64)e << (LOG_M - Kc));
+    for (int e = tid; e < C / 2; e += nt) twi[e] = t.inv_hi[(size_t)e << (LOG_T - Kc)];
   if (mode != INTT_COSET_NAT)
-    for (int e = tid; e < Cp / 2; e += nt) twf[e] = tpow(t.fwd_lo, t.fwd_hi, (u64)e << (LOG_M - Kc - r));
+    for (int e = tid; e < Cp / 2; e += nt) twf[e] = t.fwd_hi[(size_t)e << (LOG_T - Kc - r)];
   if (mode == FROM_COEFFS_LDE) {
     for (int off = tid; off < C; off += nt) {
       u64 m = blk * C + off;
-      small[off] = src[gl::brev32((u32)m, L)];
+      small[NTT_PHYS(off)] = src[gl::brev32((u32)m, L)];
     }
   } else {
-    for (int off = tid; off < C; off += nt) small[off] = src[blk * C + off];
+    for (int off = tid; off < C; off += nt) small[NTT_PHYS(off)] = src[blk * C + off];
   }
   __syncthreads();
-  if (mode != FROM_COEFFS_LDE) {
-    for (int s = 0; s < Kc; s++) {
-      const int half = C >> (s + 1);
-      for (int b = tid; b < C / 2; b += nt) {
-        int j = b & (half - 1), grp = b / half;
-        int i0 = grp * 2 * half + j, i1 = i0 + half;
-        u64 a = small[i0], bb = small[i1];
-        small[i0] = gl::add(a, bb);
-        small[i1] = gl::mul(gl::sub(a, bb), twi[j << s]);
-      }
-      __syncthreads();
-    }
-  }
+  if (mode != FROM_COEFFS_LDE) tile_stages<true, 0>(small, twi, Kc, 0, Kc, tid, nt);
   if (mode == INTT_COSET_NAT) {
     for (int off = tid; off < C; off += nt) {
       u64 m = blk * C + off;
       u64 i = gl::brev32((u32)m, L);
-      u64 sc = gl::mul(tpow(t.ish_lo, t.ish_hi, i), ninv);
-      dst[i] = gl::mul(small[off], sc);
+      u64 sc = gl::mul_lazy(tpow(t.ish_lo, t.ish_hi, i), ninv);
+      dst[i] = gl::mul(small[NTT_PHYS(off)], sc);
     }
     return;
   }
@@ -126,63 +183,53 @@ static __global__ void __launch_bounds__(256) k_ntt_fused(const u64* __restrict_
     u64 m = blk * C + off;
     u64 i = gl::brev32((u32)m, L);
     u64 sc = tpow(t.sh_lo, t.sh_hi, i);
-    if (mode == FROM_VALUES_LDE) sc = gl::mul(sc, ninv);
-    u64 v = gl::mul(small[off], sc);
-    for (int q = 0; q < (1 << r); q++) big[(off << r) + q] = v;
+    if (mode == FROM_VALUES_LDE) sc = gl::mul_lazy(sc, ninv);
+    u64 v = gl::mul_lazy(small[NTT_PHYS(off)], sc);
+    for (int q = 0; q < (1 << r); q++) big[NTT_PHYS((off << r) + q)] = v;
   }
   __syncthreads();
-  for (int s = r; s < Kc + r; s++) {
-    const int half = 1 << s;
-    for (int b = tid; b < Cp / 2; b += nt) {
-      int j = b & (half - 1), grp = b >> s;
-      int i0 = grp * 2 * half + j, i1 = i0 + half;
-      u64 a = big[i0], x = gl::mul(big[i1], twf[j << (Kc + r - 1 - s)]);
-      big[i0] = gl::add(a, x);
-      big[i1] = gl::sub(a, x);
-    }
-    __syncthreads();
-  }
+  tile_stages<false, 0>(big, twf, Kc + r, r, Kc + r, tid, nt);
   const u64 i1 = gl::brev32((u32)blk, K1);
   for (int off = tid; off < Cp; off += nt) {
-    u64 v = big[off];
-    if (K1 > 0) v = gl::mul(v, tpow(t.fwd_lo, t.fwd_hi, (i1 * off) << (LOG_M - L - r)));
+    u64 v = big[NTT_PHYS(off)];
+    if (K1 > 0)
+      v = gl::mul_lazy(v, tpow(t.fwd_lo, t.fwd_hi, (i1 * off) << (LOG_M - L - r)));  // pass D canonicalises
+    else
+      v = gl::canonical(v);
     dst[blk * Cp + off] = v;
   }
 }
 
-// pass D: forward DIT over the block index (rows at stride Cp), in place
-static __global__ void __launch_bounds__(256) k_ntt_pass_d(u64* __restrict__ data, int K1, size_t Cp, size_t stride,
+// pass D: forward DIT over the block index (rows at stride Cp), in place; writes canonical values
+static __global__ void __launch_bounds__(512) k_ntt_pass_d(u64* __restrict__ data, int K1, size_t Cp, size_t stride,
                                                     Tables t) {
   extern __shared__ u64 sm[];
   const int R = 1 << K1;
-  u64* tw = sm + (size_t)R * TC;
+  u64* tw = sm + NTT_PHYS(R * TC) + 16;
   const int tid = threadIdx.x, nt = blockDim.x;
   const size_t c0 = (size_t)blockIdx.x * TC;
   u64* col = data + (size_t)blockIdx.y * stride;
-  for (int e = tid; e < R / 2; e += nt) tw[e] = tpow(t.fwd_lo, t.fwd_hi, (u64)e << (LOG_M - K1));
+  for (int e = tid; e < R / 2; e += nt) tw[e] = t.fwd_hi[(size_t)e << (LOG_T - K1)];
   for (int idx = tid; idx < R * TC; idx += nt) {
-    int rr = idx / TC, c = idx % TC;
-    sm[idx] = col[(size_t)rr * Cp + c0 + c];
+    int rr = idx >> LOG_TC, c = idx & (TC - 1);
+    sm[NTT_PHYS(idx)] = col[(size_t)rr * Cp + c0 + c];
   }
   __syncthreads();
-  for (int s = 0; s < K1; s++) {
-    const int half = 1 << s;
-    for (int b = tid; b < (R / 2) * TC; b += nt) {
-      int c = b % TC, p = b / TC;
-      int j = p & (half - 1), grp = p >> s;
-      int i0 = (grp * 2 * half + j) * TC + c, i1 = i0 + half * TC;
-      u64 a = sm[i0], x = gl::mul(sm[i1], tw[j << (K1 - 1 - s)]);
-      sm[i0] = gl::add(a, x);
-      sm[i1] = gl::sub(a, x);
-    }
-    __syncthreads();
-  }
+  tile_stages<false, LOG_TC>(sm, tw, K1, 0, K1, tid, nt);
   for (int idx = tid; idx < R * TC; idx += nt) {
-    int rr = idx / TC, c = idx % TC;
-    col[(size_t)rr * Cp + c0 + c] = sm[idx];
+    int rr = idx >> LOG_TC, c = idx & (TC - 1);
+    col[(size_t)rr * Cp + c0 + c] = gl::canonical(sm[NTT_PHYS(idx)]);
   }
 }
 
+static inline size_t fused_smem_words(int C, int Cp) {
+  return (size_t)NTT_PHYS(C) + 16 + NTT_PHYS(Cp) + 16 + Cp / 2 + C / 2;
+}
+// one radix-8 item per thread and round where the tile is large enough
+static inline unsigned tile_threads(int K1) {
+  int items = ((1 << K1) * TC) >> 3;
+  return items >= 512 ? 512u : items >= 64 ? (unsigned)items : 64u;
+}
 static bool g_ntt_attr_set = false;
 static inline void set_smem_attrs() {
   if (g_ntt_attr_set) return;
@@ -253,8 +300,8 @@ static inline void lde_columns(const TableSet& ts, const u64* in, size_t in_stri
   size_t fused_stride = in_stride;
   if (mode == FROM_VALUES_LDE && p.K1 > 0) {
     dim3 grid((unsigned)((n >> p.K1) / TC), ncols);
-    size_t smem = ((size_t)(1 << p.K1) * TC + (1 << p.K1) / 2) * 8;
-    k_ntt_pass_a<<<grid, 256, smem, s>>>(in, scratch, L, p.K1, in_stride, n, ts.t);
+    size_t smem = tile_smem_words(p.K1) * 8;
+    k_ntt_pass_a<<<grid, tile_threads(p.K1), smem, s>>>(in, scratch, L, p.K1, in_stride, n, ts.t);
     g_pb_launches++;
     pb_check_last("ntt pass A");
     fused_in = scratch;
@@ -262,15 +309,15 @@ static inline void lde_columns(const TableSet& ts, const u64* in, size_t in_stri
   }
   {
     dim3 grid((unsigned)(n >> p.Kc), ncols);
-    size_t smem = ((size_t)C + Cp + Cp / 2 + C / 2) * 8;
+    size_t smem = fused_smem_words(C, Cp) * 8;
     k_ntt_fused<<<grid, 256, smem, s>>>(fused_in, out, L, p.Kc, r, fused_stride, out_stride, ts.t, ninv, mode);
     g_pb_launches++;
     pb_check_last("ntt fused");
   }
   if (p.K1 > 0) {
     dim3 grid((unsigned)(Cp / TC), ncols);
-    size_t smem = ((size_t)(1 << p.K1) * TC + (1 << p.K1) / 2) * 8;
-    k_ntt_pass_d<<<grid, 256, smem, s>>>(out, p.K1, (size_t)Cp, out_stride, ts.t);
+    size_t smem = tile_smem_words(p.K1) * 8;
+    k_ntt_pass_d<<<grid, tile_threads(p.K1), smem, s>>>(out, p.K1, (size_t)Cp, out_stride, ts.t);
     g_pb_launches++;
     pb_check_last("ntt pass D");
   }
@@ -304,8 +351,8 @@ static inline void coset_intt_columns(const TableSet& ts, const u64* in, size_t 
   size_t fused_stride = in_stride;
   if (p.K1 > 0) {
     dim3 grid((unsigned)((n >> p.K1) / TC), ncols);
-    size_t smem = ((size_t)(1 << p.K1) * TC + (1 << p.K1) / 2) * 8;
-    k_ntt_pass_a<<<grid, 256, smem, s>>>(in, scratch, L, p.K1, in_stride, n, ts.t);
+    size_t smem = tile_smem_words(p.K1) * 8;
+    k_ntt_pass_a<<<grid, tile_threads(p.K1), smem, s>>>(in, scratch, L, p.K1, in_stride, n, ts.t);
     g_pb_launches++;
     pb_check_last("intt pass A");
     fused_in = scratch;
@@ -313,7 +360,7 @@ static inline void coset_intt_columns(const TableSet& ts, const u64* in, size_t 
   }
   dim3 grid((unsigned)(n >> p.Kc), ncols);
   const int C = 1 << p.Kc;
-  size_t smem = ((size_t)C + C + C / 2 + C / 2) * 8;
+  size_t smem = fused_smem_words(C, C) * 8;
   k_ntt_fused<<<grid, 256, smem, s>>>(fused_in, out, L, p.Kc, 0, fused_stride, out_stride, ts.t, ninv, INTT_COSET_NAT);
   g_pb_launches++;
   pb_check_last("intt fused");
