@@ -111,6 +111,15 @@ int pb254_prove_dev(pb254_ctx* ctx, int kind, const uint64_t* d_inputs, const ui
 int pb254_prove_trace(pb254_ctx* ctx, int kind, const uint64_t* trace_cols, size_t n_rows, const pb254_config* cfg,
                       int keep_debug, pb254_proof** out);
 void pb254_proof_free(pb254_proof* proof);
+
+/* ---- verification (host; the reference verifies on the CPU as well) ----------------------------- */
+/* verify(stark, config, ctls, proof, public_inputs = [], extra_looking_values)
+ * (src/starks/common/verifier.rs:32-98) on a serialized proof. The extra looking values are recomputed
+ * natively from the batch (inputs / timestamps, same wire format as pb254_prove), as run_once does with
+ * g1_generate_ctl_values (src/starks/curves/g1/scalar_mul_ctl.rs:57-80). Returns PB254_OK or PB254_E_VERIFY
+ * (pb254_last_error() names the failed check). Needs no context and no GPU. */
+int pb254_verify(const uint64_t* proof_words, size_t n_words, const uint64_t* inputs, const uint64_t* timestamps,
+                 size_t n_inputs);
 /* Serialized StarkProofWithMetadata: little-endian u64 words, field order of SURVEY.md C.7 behind a
  * 10-word header {magic, kind, degree_bits, config[7]} (layout in DESIGN.md). */
 size_t pb254_proof_words(const pb254_proof* proof);

@@ -10,6 +10,7 @@ unsigned long long g_pb_launches = 0;
 #include "merkle.cuh"
 #include "tracegen.h"
 #include "prover.cuh"
+#include "verify.cuh"
 
 struct pb254_proof {
   prover::ProofData data;
@@ -330,6 +331,16 @@ int pb254_prove_trace(pb254_ctx* c, int kind, const uint64_t* trace_cols, size_t
     pb_sync(c->stream);
     c->times.resolve();
     *out = pf;
+  });
+}
+
+// verify(stark, config, ctls, proof, [], extra_looking_values) of src/starks/common/verifier.rs:32-98, with the
+// extra looking values recomputed natively from the batch as run_once does (g1/scalar_mul_ctl.rs:57-80).
+int pb254_verify(const uint64_t* proof_words, size_t n_words, const uint64_t* inputs, const uint64_t* timestamps,
+                 size_t n_inputs) {
+  return guarded([&] {
+    if (!proof_words || !inputs || !timestamps) throw Pb254Error(PB254_E_BAD_ARG, "null argument");
+    verify::verify_proof(proof_words, n_words, inputs, timestamps, n_inputs);
   });
 }
 

@@ -103,6 +103,16 @@ class Library:
         return self.lib.pb254_trace_rows(n_inputs, min_rows)
 
 
+    def verify(self, proof_words, inputs, timestamps) -> bool:
+        """pb254_verify: True, or raises Pb254Error(E_VERIFY / ...) naming the failed check."""
+        w = _u64(proof_words)
+        inputs = _u64(inputs)
+        timestamps = _u64(timestamps)
+        self.check(self.lib.pb254_verify(_p(w), C.c_size_t(w.size), _p(inputs), _p(timestamps),
+                                         C.c_size_t(inputs.shape[0])))
+        return True
+
+
 _default = None
 
 

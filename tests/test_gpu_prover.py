@@ -88,3 +88,16 @@ def test_config2_shape_verifies(gpu_ctx, oracle, kind):
     w = gpu_ctx.prove(kind, inp, ts).words()
     assert int(w[2]) == 19
     assert oracle.verify(w, inp, ts)
+
+
+@pytest.mark.parametrize("kind,k", [(I.KIND_G2, 1), (I.KIND_G1, 3)])
+def test_product_verifier_accepts_gpu_proofs(gpu_ctx, kind, k):
+    """pb254_verify (csrc/verify.cuh, host) on proofs from the GPU prover; rejects a flipped opening."""
+    from plonky2_bn254_b200 import ffi
+    inp, ts = I.make_inputs(kind, k, I.config_seed(80 + kind))
+    w = gpu_ctx.prove(kind, inp, ts).words()
+    assert gpu_ctx.L.verify(w, inp, ts)
+    w[300] ^= np.uint64(1)
+    with pytest.raises(ffi.Pb254Error) as e:
+        gpu_ctx.L.verify(w, inp, ts)
+    assert e.value.code == 7
