@@ -1,0 +1,74 @@
+//! Raw bindings of `include/pb254.h`. One item per C declaration, same order.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_double, c_int, c_void};
+
+pub const PB254_KIND_G1: c_int = 0;
+pub const PB254_KIND_G2: c_int = 1;
+pub const PB254_KIND_FQ: c_int = 2;
+
+pub const PB254_OK: c_int = 0;
+pub const PB254_E_SCALAR_RANGE: c_int = 1;
+pub const PB254_E_INFINITY: c_int = 2;
+pub const PB254_E_NOT_CANONICAL: c_int = 3;
+pub const PB254_E_CUDA: c_int = 4;
+pub const PB254_E_OOM: c_int = 5;
+pub const PB254_E_BAD_ARG: c_int = 6;
+pub const PB254_E_VERIFY: c_int = 7;
+
+/// `StarkConfig` (starky config.rs); `standard_fast_config()` = {1, 4, 2, 84, 16, 4, 5}.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct pb254_config {
+    pub rate_bits: u32,
+    pub cap_height: u32,
+    pub num_challenges: u32,
+    pub num_query_rounds: u32,
+    pub pow_bits: u32,
+    pub arity_bits: u32,
+    pub final_poly_bits: u32,
+}
+
+#[repr(C)]
+pub struct pb254_ctx {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct pb254_proof {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn pb254_config_standard_fast(out: *mut pb254_config);
+    pub fn pb254_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut pb254_ctx) -> c_int;
+    pub fn pb254_ctx_destroy(ctx: *mut pb254_ctx);
+    pub fn pb254_last_error() -> *const c_char;
+    pub fn pb254_launch_count() -> u64;
+    pub fn pb254_timing_count(ctx: *mut pb254_ctx) -> c_int;
+    pub fn pb254_timing_name(ctx: *mut pb254_ctx, i: c_int) -> *const c_char;
+    pub fn pb254_timing_ms(ctx: *mut pb254_ctx, i: c_int) -> c_double;
+    pub fn pb254_trace_width(kind: c_int) -> c_int;
+    pub fn pb254_input_words(kind: c_int) -> c_int;
+    pub fn pb254_num_aux(kind: c_int, num_challenges: u32) -> c_int;
+    pub fn pb254_trace_rows(n_inputs: usize, min_rows: usize) -> usize;
+    pub fn pb254_poseidon_permute(ctx: *mut pb254_ctx, states_in: *const u64, n: usize, states_out: *mut u64) -> c_int;
+    pub fn pb254_lde_batch(ctx: *mut pb254_ctx, values: *const u64, cols: usize, n: usize, rate_bits: u32,
+                           from_coeffs: c_int, lde_out: *mut u64) -> c_int;
+    pub fn pb254_commit(ctx: *mut pb254_ctx, values: *const u64, cols: usize, n: usize, rate_bits: u32,
+                        cap_height: u32, from_coeffs: c_int, cap_out: *mut u64, digests_out: *mut u64) -> c_int;
+    pub fn pb254_generate_trace(ctx: *mut pb254_ctx, kind: c_int, inputs: *const u64, timestamps: *const u64,
+                                n_inputs: usize, min_rows: usize, cols_out: *mut u64) -> c_int;
+    pub fn pb254_prove(ctx: *mut pb254_ctx, kind: c_int, inputs: *const u64, timestamps: *const u64, n_inputs: usize,
+                       min_rows: usize, cfg: *const pb254_config, keep_debug: c_int, out: *mut *mut pb254_proof) -> c_int;
+    pub fn pb254_prove_dev(ctx: *mut pb254_ctx, kind: c_int, d_inputs: *const u64, d_timestamps: *const u64,
+                           n_inputs: usize, min_rows: usize, cfg: *const pb254_config, keep_debug: c_int,
+                           out: *mut *mut pb254_proof) -> c_int;
+    pub fn pb254_prove_trace(ctx: *mut pb254_ctx, kind: c_int, trace_cols: *const u64, n_rows: usize,
+                             cfg: *const pb254_config, keep_debug: c_int, out: *mut *mut pb254_proof) -> c_int;
+    pub fn pb254_proof_free(proof: *mut pb254_proof);
+    pub fn pb254_verify(proof_words: *const u64, n_words: usize, inputs: *const u64, timestamps: *const u64,
+                        n_inputs: usize) -> c_int;
+    pub fn pb254_proof_words(proof: *const pb254_proof) -> usize;
+    pub fn pb254_proof_data(proof: *const pb254_proof) -> *const u64;
+    pub fn pb254_proof_debug_words(proof: *const pb254_proof, which: c_int) -> usize;
+    pub fn pb254_proof_debug_data(proof: *const pb254_proof, which: c_int) -> *const u64;
+}
