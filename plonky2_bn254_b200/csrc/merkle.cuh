@@ -84,32 +84,28 @@ __device__ __forceinline__ void stage_rc2(u64* rc2) {
   __syncthreads();
 }
 
-// one thread per LDE row; the next 8 columns are loaded while the current permutation runs
+// one thread per LDE row
 __global__ void __launch_bounds__(128, 6) k_leaf_hash(const u64* __restrict__ lde, size_t stride, int W, int log_n,
                                                    Digest* __restrict__ out) {
-  __shared__ u64 rc2[poseidon::RC2_WORDS];
+  __shared__ __align__(16) u64 rc2[poseidon::RC2_WORDS];
   stage_rc2(rc2);
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ((size_t)1 << log_n)) return;
   const u64* p = lde + j;
-  u64 s[12], nx[8];
+  u64 s[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = 0;
   const int chunks = (W + 7) / 8;
-#pragma unroll
-  for (int k = 0; k < 8; k++) nx[k] = k < W ? p[(size_t)k * stride] : 0;
+  // No software prefetch: a warp spends ~10^5 cycles in one permutation, three orders of magnitude more than
+  // the latency of the 8 loads in front of it, and the 16 registers are worth more than the overlap.
 #pragma unroll 1
   for (int c = 0; c < chunks; c++) {
     // hash_no_pad overwrites the first min(8, remaining) rate lanes with the chunk
     const int len = W - 8 * c;
+    const u64* q = p + (size_t)c * 8 * stride;
 #pragma unroll
     for (int k = 0; k < 8; k++)
-      if (k < len) s[k] = nx[k];
-    const u64* q = p + (size_t)(c + 1) * 8 * stride;
-    const int nlen = len - 8;
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (k < nlen) nx[k] = q[(size_t)k * stride];
+      if (k < len) s[k] = q[(size_t)k * stride];
     poseidon::lazy::permute(s, rc2);
   }
   Digest d;
@@ -119,7 +115,7 @@ __global__ void __launch_bounds__(128, 6) k_leaf_hash(const u64* __restrict__ ld
 }
 
 __global__ void __launch_bounds__(128, 6) k_level(const Digest* __restrict__ child, Digest* __restrict__ parent, size_t n) {
-  __shared__ u64 rc2[poseidon::RC2_WORDS];
+  __shared__ __align__(16) u64 rc2[poseidon::RC2_WORDS];
   stage_rc2(rc2);
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -114,54 +114,18 @@ PB_HD void permute_generic(u64 s[12]) {
 
 #if !PB_HOSTSIM
 // ---- device form: lazy representatives, PTX carry chains, compact code -----------------------------
-// Split table: constant k of (round r, lane i) as RC2[(r*12 + i)*2 + {0,1}] = {k & (2^32-1), k >> 32};
-// block r = 30 is all zero. Kernels that hash a lot stage it into shared memory (RC2_WORDS u64s).
-static constexpr int RC2_WORDS = (N_ROUNDS + 1) * WIDTH * 2;
-static __constant__ u64 RC2_DEV[RC2_WORDS] = {
+// Piece table: constant k of (round r, lane i) as four u32 RC2[(r*12 + i)*2 ..] = {k0, k1, k2, k3}, its 16-bit
+// pieces (block r = 30 is all zero), followed by the 12 round-0 constants as plain u64. Kernels that hash a
+// lot stage it into shared memory (RC2_WORDS u64s, 16-byte aligned).
+static constexpr int RC2_WORDS = (N_ROUNDS + 1) * WIDTH * 2 + WIDTH;
+static __constant__ __align__(16) u64 RC2_DEV[RC2_WORDS] = {
 #include "poseidon_constants_split.inc"
 };
 
 namespace lazy {
 
-// a * b mod p for arbitrary u64 representatives; result is an arbitrary u64 representative.
-// Four full-rate IMAD.WIDE.U32 products (mul.hi / IMAD.HI and carry-out IMADs are half rate on B200,
-// tools/microbench/pipe_rates.cu) summed by carry chains into (x3 x2 x1 x0), then
-//   x0 + x1 2^32 + x2 2^64 + x3 2^96 == (x1:x0) - x3 + x2 (2^32 - 1)  (mod p).
-__device__ __forceinline__ u64 mul(u64 a, u64 b) {
-  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-  u32 r0, r1;
-  asm("{\n\t"
-      ".reg .u32 x0, x1, x2, x3, m, l, h, c;\n\t"
-      ".reg .u64 P, Q, R, S; .reg .u32 p1, q0, q1, s0, s1, t0, t1;\n\t"
-      "mul.wide.u32 P, %2, %4;\n\t"
-      "mul.wide.u32 Q, %2, %5;\n\t"
-      "mul.wide.u32 R, %3, %4;\n\t"
-      "mul.wide.u32 S, %3, %5;\n\t"
-      "mov.b64 {x0, p1}, P; mov.b64 {q0, q1}, Q; mov.b64 {t0, t1}, R; mov.b64 {s0, s1}, S;\n\t"
-      "add.cc.u32   x1, p1, q0;\n\t"
-      "addc.cc.u32  x2, q1, s0;\n\t"
-      "addc.u32     x3, s1, 0;\n\t"
-      "add.cc.u32   x1, x1, t0;\n\t"
-      "addc.cc.u32  x2, x2, t1;\n\t"
-      "addc.u32     x3, x3, 0;\n\t"
-      "sub.cc.u32   %0, x0, x3;\n\t"
-      "subc.cc.u32  %1, x1, 0;\n\t"
-      "subc.u32     m, 0, 0;\n\t"
-      "sub.cc.u32   %0, %0, m;\n\t"
-      "subc.u32     %1, %1, 0;\n\t"
-      "sub.cc.u32   l, 0, x2;\n\t"
-      "subc.u32     h, x2, 0;\n\t"
-      "add.cc.u32   %0, %0, l;\n\t"
-      "addc.cc.u32  %1, %1, h;\n\t"
-      "addc.u32     c, 0, 0;\n\t"
-      "sub.u32      c, 0, c;\n\t"
-      "add.cc.u32   %0, %0, c;\n\t"
-      "addc.u32     %1, %1, 0;\n\t"
-      "}"
-      : "=&r"(r0), "=&r"(r1)
-      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-  return ((u64)r1 << 32) | r0;
-}
+__device__ __forceinline__ u64 mul(u64 a, u64 b) { return gl::mul_lazy(a, b); }
+
 __device__ __forceinline__ u64 sbox(u64 x) {
   const u64 x2 = mul(x, x), x4 = mul(x2, x2), x3 = mul(x, x2);
   return mul(x3, x4);
@@ -205,13 +169,11 @@ __device__ __forceinline__ void dp_row(u32 acc[4], const u32 (*X)[4]) {
 }
 template <int R>
 __device__ __forceinline__ void mds_rows(u64 s[12], const u32 (*X)[4], const u64* rc2) {
-  u32 acc[4] = {0, 0, 0, 0};
+  // the next round's constant enters as the initial value of the four piece accumulators
+  const uint4 k = *reinterpret_cast<const uint4*>(rc2 + 2 * R);
+  u32 acc[4] = {k.x, k.y, k.z, k.w};
   dp_row<R, 0>(acc, X);
-  u64 al = rc2[2 * R], ah = rc2[2 * R + 1];
-  asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(al) : "r"(acc[0]));
-  asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(al) : "r"(acc[1]));
-  asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(ah) : "r"(acc[2]));
-  asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(ah) : "r"(acc[3]));
+  const u64 al = (u64)acc[0] + ((u64)acc[1] << 16), ah = (u64)acc[2] + ((u64)acc[3] << 16);
   s[R] = reduce_split(al, ah);
   if constexpr (R + 1 < 12) mds_rows<R + 1>(s, X, rc2);
 }
@@ -234,7 +196,7 @@ __device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {
 __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
 #pragma unroll
   for (int i = 0; i < 12; i++) {  // inputs are canonical: s + k wraps at most once
-    const u64 k = rc2[2 * i] | (rc2[2 * i + 1] << 32);
+    const u64 k = rc2[N_ROUNDS * 24 + 24 + i];
     u64 t = s[i] + k;
     if (t < k) t += gl::EPS;
     s[i] = t;

@@ -23,6 +23,10 @@ __global__ void k_rate(u32* out, int iters, u32 seed) {
       if (MODE == 7) asm volatile("shf.l.wrap.b32 %0, %0, %1, 5;" : "+r"(lo[j]) : "r"(hi[j]));
       if (MODE == 8) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(lo[j]) : "r"(b));
       if (MODE == 9) { asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %2, %0, p;}" : "+r"(lo[j]) : "r"(a), "r"(b)); }
+      if (MODE == 11) asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b));
+      if (MODE == 12) asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b));
+      if (MODE == 13) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(lo[j]) : "r"(b));
+      if (MODE == 14) { asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b)); asm volatile("add.cc.u32 %0, %0, %1;\n\taddc.u32 %0, %0, %1;" : "+r"(hi[j]) : "r"(b)); }
       if (MODE == 10) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;\n\taddc.u32 %0, %0, 0;" : "+r"(lo[j]), "+r"(hi[j]) : "r"(a), "r"(b));
     }
   }
@@ -65,6 +69,10 @@ int main() {
   run<6>("lop3", 1, d, e0, e1);
   run<7>("shf.l.wrap", 1, d, e0, e1);
   run<8>("mul.hi.u32", 1, d, e0, e1);
+  run<11>("dp2a.lo.u32.u32 (IDP.2A)", 1, d, e0, e1);
+  run<12>("dp4a.u32.u32 (IDP.4A)", 1, d, e0, e1);
+  run<13>("prmt", 1, d, e0, e1);
+  run<14>("dp2a + (add.cc, addc) interleaved", 3, d, e0, e1);
   run<9>("setp + selp", 2, d, e0, e1);
   printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;

@@ -2,6 +2,20 @@
 #include "../../plonky2_bn254_b200/csrc/compat.cuh"
 namespace lazy {
 static constexpr u64 EPS = 0xFFFFFFFFULL, P = 0xFFFFFFFF00000001ULL;
+#ifdef MUL_I128
+__device__ __forceinline__ u64 mulw(u32 a, u32 b) { u64 r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  const u64 P = mulw(a0, b0), Q = mulw(a0, b1), R = mulw(a1, b0), S = mulw(a1, b1);
+  unsigned __int128 prod = (unsigned __int128)P + (((unsigned __int128)Q + R) << 32) + ((unsigned __int128)S << 64);
+  const u64 lo = (u64)prod, hi = (u64)(prod >> 64);
+  const u32 x2 = (u32)hi, x3 = (u32)(hi >> 32);
+  __int128 V = (__int128)lo - x3 - x2 + ((__int128)x2 << 32);
+  const u64 r = (u64)V;
+  const long long w = (long long)(V >> 64);
+  return r + (u64)(w * 0xFFFFFFFFLL);
+}
+#else
 __device__ __forceinline__ u64 mul(u64 a, u64 b) {
   const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
   u32 r0, r1;
@@ -37,6 +51,7 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
       : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return ((u64)r1 << 32) | r0;
 }
+#endif
 __device__ __forceinline__ u64 sbox(u64 x) {
   const u64 x2 = mul(x, x), x4 = mul(x2, x2), x3 = mul(x, x2);
   return mul(x3, x4);
@@ -77,6 +92,13 @@ __device__ __forceinline__ void dp_row(u32 acc[4], const u32 (*X)[4]) {
 }
 template <int R>
 __device__ __forceinline__ void mds_rows(u64 s[12], const u32 (*X)[4], const u64* rc2) {
+#ifdef RC_PIECES
+  // the next round's constant enters as the initial value of the four piece accumulators
+  const uint4 k = *reinterpret_cast<const uint4*>(rc2 + 2 * R);
+  u32 acc[4] = {k.x, k.y, k.z, k.w};
+  dp_row<R, 0>(acc, X);
+  const u64 al = (u64)acc[0] + ((u64)acc[1] << 16), ah = (u64)acc[2] + ((u64)acc[3] << 16);
+#else
   u32 acc[4] = {0, 0, 0, 0};
   dp_row<R, 0>(acc, X);
   u64 al = rc2[2 * R], ah = rc2[2 * R + 1];
@@ -84,6 +106,7 @@ __device__ __forceinline__ void mds_rows(u64 s[12], const u32 (*X)[4], const u64
   asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(al) : "r"(acc[1]));
   asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(ah) : "r"(acc[2]));
   asm("mad.wide.u32 %0, %1, 65536, %0;" : "+l"(ah) : "r"(acc[3]));
+#endif
   s[R] = reduce_split(al, ah);
   if constexpr (R + 1 < 12) mds_rows<R + 1>(s, X, rc2);
 }
@@ -103,7 +126,11 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
   // rc2[0] block holds round 0's constants: s += rc (canonical inputs)
 #pragma unroll
   for (int i = 0; i < 12; i++) {
+#ifdef RC_PIECES
+    u64 k = rc2[31 * 24 + i];
+#else
     u64 k = rc2[2 * i] | (rc2[2 * i + 1] << 32);
+#endif
     u64 t = s[i] + k;
     if (t < k) t += EPS;
     s[i] = t;
@@ -137,8 +164,8 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
 #define MINB 1
 #endif
 __global__ void __launch_bounds__(128, MINB) k_compact(const u64* in, u64* out, const u64* rc2g, int reps) {
-  __shared__ u64 rc2[31 * 24];
-  for (int i = threadIdx.x; i < 31 * 24; i += blockDim.x) rc2[i] = rc2g[i];
+  __shared__ __align__(16) u64 rc2[31 * 24 + 12];
+  for (int i = threadIdx.x; i < 31 * 24 + 12; i += blockDim.x) rc2[i] = rc2g[i];
   __syncthreads();
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   u64 s[12];
@@ -182,8 +209,13 @@ int main() {
   u64 x = 88172645463325252ULL;
   for (auto& v : h) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = x % 0xFFFFFFFF00000001ULL; }
   for (int k = 0; k < 12; k++) { h[k] = 0; h[12 + k] = k; h[24 + k] = 0xFFFFFFFF00000000ULL; }
-  std::vector<u64> rc2(31 * 24, 0);
+  std::vector<u64> rc2(31 * 24 + 12, 0);
+#ifdef RC_PIECES
+  for (int i = 0; i < 360; i++) { u64 k = poseidon::RC_HOST[i]; rc2[2 * i] = (k & 0xFFFF) | (((k >> 16) & 0xFFFF) << 32); rc2[2 * i + 1] = ((k >> 32) & 0xFFFF) | ((k >> 48) << 32); }
+  for (int i = 0; i < 12; i++) rc2[31 * 24 + i] = poseidon::RC_HOST[i];
+#else
   for (int i = 0; i < 360; i++) { rc2[2 * i] = poseidon::RC_HOST[i] & 0xFFFFFFFFULL; rc2[2 * i + 1] = poseidon::RC_HOST[i] >> 32; }
+#endif
   u64 *din, *dout, *dout2, *drc;
   cudaMalloc(&din, n * 96); cudaMalloc(&dout, n * 96); cudaMalloc(&dout2, n * 96); cudaMalloc(&drc, rc2.size() * 8);
   cudaMemcpy(din, h.data(), n * 96, cudaMemcpyHostToDevice);
