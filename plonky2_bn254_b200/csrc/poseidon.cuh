@@ -131,25 +131,6 @@ __device__ __forceinline__ u64 sbox(u64 x) {
   return mul(x3, x4);
 }
 
-// al + 2^32 ah with al, ah < 2^42  ->  u64 representative
-__device__ __forceinline__ u64 reduce_split(u64 al, u64 ah) {
-  const u32 h0 = (u32)ah, h1 = (u32)(ah >> 32);  // value = al + h0 2^32 + h1 2^64
-  u64 t = al;
-  asm("mad.wide.u32 %0, %1, 0xffffffff, %0;" : "+l"(t) : "r"(h1));  // + h1 (2^32 - 1); < 2^43
-  u32 r0 = (u32)t, r1 = (u32)(t >> 32);
-  asm("{\n\t"
-      ".reg .u32 c;\n\t"
-      "add.cc.u32   %1, %1, %2;\n\t"
-      "addc.u32     c, 0, 0;\n\t"
-      "sub.u32      c, 0, c;\n\t"
-      "add.cc.u32   %0, %0, c;\n\t"    // wrapped by 2^64: add 2^32 - 1 (the wrapped value is < 2^43)
-      "addc.u32     %1, %1, 0;\n\t"
-      "}"
-      : "+r"(r0), "+r"(r1)
-      : "r"(h0));
-  return ((u64)r1 << 32) | r0;
-}
-
 // s <- MDS s + (next round's constants); rc2 = 24 words of the split table.
 // MDS on 16-bit pieces with dp2a: lanes are cut into four 16-bit pieces; pieces of the same weight of two
 // neighbouring lanes are packed into one register, and one dp2a adds two (piece x 6-bit entry) products to
@@ -173,8 +154,29 @@ __device__ __forceinline__ void mds_rows(u64 s[12], const u32 (*X)[4], const u64
   const uint4 k = *reinterpret_cast<const uint4*>(rc2 + 2 * R);
   u32 acc[4] = {k.x, k.y, k.z, k.w};
   dp_row<R, 0>(acc, X);
-  const u64 al = (u64)acc[0] + ((u64)acc[1] << 16), ah = (u64)acc[2] + ((u64)acc[3] << 16);
-  s[R] = reduce_split(al, ah);
+  // value = acc0 + acc1 2^16 + acc2 2^32 + acc3 2^48 (acc < 2^25) -> u64 representative. The layer is bound by
+  // the FMA pipe (288 IDP), so this part uses the ALU pipe only: byte permutes for the 16-bit shifts (ptxas
+  // turns shifts by 16 into IMAD.SHL / half-rate IMAD.HI) and carry chains.
+  const u32 t1 = __byte_perm(acc[1], 0, 0x1044), u1 = __byte_perm(acc[1], 0, 0x4432);
+  const u32 t3 = __byte_perm(acc[3], 0, 0x1044), u3 = __byte_perm(acc[3], 0, 0x4432);
+  u32 lo, hi;
+  asm("{\n\t"
+      ".reg .u32 w2, c;\n\t"
+      "add.cc.u32   %0, %2, %3;\n\t"   // w0 = acc0 + (acc1 << 16)
+      "addc.u32     %1, %4, %5;\n\t"   // w1 = (acc1 >> 16) + acc2 + carry      (< 2^26)
+      "add.cc.u32   %1, %1, %6;\n\t"   // w1 += acc3 << 16
+      "addc.u32     w2, %7, 0;\n\t"    // w2 = (acc3 >> 16) + carry             (< 2^10)
+      "add.cc.u32   %1, %1, w2;\n\t"   // + w2 2^32 ...
+      "addc.u32     c, 0, 0;\n\t"
+      "sub.cc.u32   %0, %0, w2;\n\t"   // ... - w2        (w2 2^64 == w2 (2^32 - 1)); cannot borrow out
+      "subc.u32     %1, %1, 0;\n\t"
+      "sub.u32      c, 0, c;\n\t"      // wrapped by 2^64: add 2^32 - 1 (the wrapped value is < 2^42)
+      "add.cc.u32   %0, %0, c;\n\t"
+      "addc.u32     %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(lo), "=&r"(hi)
+      : "r"(acc[0]), "r"(t1), "r"(u1), "r"(acc[2]), "r"(t3), "r"(u3));
+  s[R] = ((u64)hi << 32) | lo;
   if constexpr (R + 1 < 12) mds_rows<R + 1>(s, X, rc2);
 }
 __device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {

@@ -97,6 +97,33 @@ __device__ __forceinline__ void mds_rows(u64 s[12], const u32 (*X)[4], const u64
   const uint4 k = *reinterpret_cast<const uint4*>(rc2 + 2 * R);
   u32 acc[4] = {k.x, k.y, k.z, k.w};
   dp_row<R, 0>(acc, X);
+#ifdef ALU_RECOMB
+  {
+    // value = acc0 + acc1 2^16 + acc2 2^32 + acc3 2^48 (acc < 2^25) -> u64 representative, ALU pipe only
+    const u32 t1 = __byte_perm(acc[1], 0, 0x1044), u1 = __byte_perm(acc[1], 0, 0x4432);
+    const u32 t3 = __byte_perm(acc[3], 0, 0x1044), u3 = __byte_perm(acc[3], 0, 0x4432);
+    u32 lo, hi;
+    asm("{\n\t"
+        ".reg .u32 w2, c;\n\t"
+        "add.cc.u32   %0, %2, %3;\n\t"   // w0 = acc0 + (acc1 << 16)
+        "addc.u32     %1, %4, %5;\n\t"   // w1 = (acc1 >> 16) + acc2 + carry      (< 2^26)
+        "add.cc.u32   %1, %1, %6;\n\t"   // w1 += acc3 << 16
+        "addc.u32     w2, %7, 0;\n\t"    // w2 = (acc3 >> 16) + carry             (< 2^10)
+        "add.cc.u32   %1, %1, w2;\n\t"   // + w2 2^32 ...
+        "addc.u32     c, 0, 0;\n\t"
+        "sub.cc.u32   %0, %0, w2;\n\t"   // ... - w2        (w2 2^64 == w2 (2^32 - 1))
+        "subc.u32     %1, %1, 0;\n\t"
+        "sub.u32      c, 0, c;\n\t"      // wrapped by 2^64: add 2^32 - 1
+        "add.cc.u32   %0, %0, c;\n\t"
+        "addc.u32     %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi)
+        : "r"(acc[0]), "r"(t1), "r"(u1), "r"(acc[2]), "r"(t3), "r"(u3));
+    s[R] = ((u64)hi << 32) | lo;
+  }
+  if constexpr (R + 1 < 12) mds_rows<R + 1>(s, X, rc2);
+  return;
+#endif
   const u64 al = (u64)acc[0] + ((u64)acc[1] << 16), ah = (u64)acc[2] + ((u64)acc[3] << 16);
 #else
   u32 acc[4] = {0, 0, 0, 0};
