@@ -23,11 +23,22 @@ enum Mode { FROM_VALUES_LDE = 0, FROM_COEFFS_LDE = 1, INTT_COSET_NAT = 2 };
 struct Plan {
   int L, r, Kc, K1;
 };
+// Split of the L index bits between the contiguous (fused) kernel and the strided passes. Measured on B200
+// (tools/probe_commit.py, PB254_KC sweep): a 2^9 fused block with 2^10-row strided tiles is best at 2^19,
+// and strided tiles beyond 2^10 rows (> 64 KB of shared memory, one CTA per SM) lose more than larger
+// fused blocks cost; so Kc = max(9, L - 10). PB254_KC overrides it for experiments.
 static inline Plan make_plan(int L, int r) {
   Plan p;
   p.L = L;
   p.r = r;
-  p.Kc = L < KC_MAX ? L : KC_MAX;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("PB254_KC");
+    forced = e ? atoi(e) : 0;
+  }
+  p.Kc = forced > 0 ? forced : (L - 10 > 9 ? L - 10 : 9);
+  if (p.Kc > L) p.Kc = L;
+  if (p.Kc + r > 13) p.Kc = 13 - r;
   if (L - p.Kc > K1_MAX) p.Kc = L - K1_MAX;
   p.K1 = L - p.Kc;
   if (p.Kc + r > 13 || L + r > LOG_M) throw Pb254Error(6, "ntt: size not supported");
@@ -143,7 +154,7 @@ static __global__ void __launch_bounds__(512) k_ntt_pass_a(const u64* __restrict
 }
 
 // fused contiguous kernel, one 2^Kc block of one column per CTA
-static __global__ void __launch_bounds__(256) k_ntt_fused(const u64* __restrict__ in, u64* __restrict__ out, int L, int Kc,
+static __global__ void __launch_bounds__(512) k_ntt_fused(const u64* __restrict__ in, u64* __restrict__ out, int L, int Kc,
                                                    int r, size_t in_stride, size_t out_stride, Tables t, u64 ninv,
                                                    int mode) {
   extern __shared__ u64 sm[];
@@ -230,6 +241,10 @@ static inline unsigned tile_threads(int K1) {
   int items = ((1 << K1) * TC) >> 3;
   return items >= 512 ? 512u : items >= 64 ? (unsigned)items : 64u;
 }
+static inline unsigned fused_threads(int Cp) {  // one radix-8 item per thread in the forward rounds
+  int t = Cp >> 3;
+  return t >= 512 ? 512u : t >= 64 ? (unsigned)t : 64u;
+}
 static bool g_ntt_attr_set = false;
 static inline void set_smem_attrs() {
   if (g_ntt_attr_set) return;
@@ -310,7 +325,7 @@ static inline void lde_columns(const TableSet& ts, const u64* in, size_t in_stri
   {
     dim3 grid((unsigned)(n >> p.Kc), ncols);
     size_t smem = fused_smem_words(C, Cp) * 8;
-    k_ntt_fused<<<grid, 256, smem, s>>>(fused_in, out, L, p.Kc, r, fused_stride, out_stride, ts.t, ninv, mode);
+    k_ntt_fused<<<grid, fused_threads(Cp), smem, s>>>(fused_in, out, L, p.Kc, r, fused_stride, out_stride, ts.t, ninv, mode);
     g_pb_launches++;
     pb_check_last("ntt fused");
   }
@@ -361,7 +376,7 @@ static inline void coset_intt_columns(const TableSet& ts, const u64* in, size_t 
   dim3 grid((unsigned)(n >> p.Kc), ncols);
   const int C = 1 << p.Kc;
   size_t smem = fused_smem_words(C, C) * 8;
-  k_ntt_fused<<<grid, 256, smem, s>>>(fused_in, out, L, p.Kc, 0, fused_stride, out_stride, ts.t, ninv, INTT_COSET_NAT);
+  k_ntt_fused<<<grid, fused_threads(C), smem, s>>>(fused_in, out, L, p.Kc, 0, fused_stride, out_stride, ts.t, ninv, INTT_COSET_NAT);
   g_pb_launches++;
   pb_check_last("intt fused");
 #endif
