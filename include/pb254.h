@@ -88,6 +88,22 @@ int pb254_lde_batch(pb254_ctx* ctx, const uint64_t* values, size_t cols, size_t 
 int pb254_commit(pb254_ctx* ctx, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits,
                  uint32_t cap_height, int from_coeffs, uint64_t* cap_out, uint64_t* digests_out);
 
+/* ---- oversized single trace across GPUs: device-pointer building blocks ------------------
+ * One committed matrix too large or too slow for one GPU is column-sharded for the LDE (no communication),
+ * exchanged once (NCCL all-to-all over NVLink, done by the host language with its own communicator) into
+ * contiguous row blocks, leaf-hashed row-locally, and the digests are all-gathered so that every rank builds
+ * the subtree under its own Merkle-cap entries. All pointers are device pointers on the context's GPU. */
+/* LDE of `cols` device-resident columns [col][n] -> [col][n << rate_bits], natural order. */
+int pb254_lde_dev(pb254_ctx* ctx, const uint64_t* d_values, size_t cols, size_t n, uint32_t rate_bits,
+                  int from_coeffs, uint64_t* d_lde_out);
+/* d_digests_out[i] = hash_or_noop(row i) for `rows` rows of the column-major matrix [cols][stride]. */
+int pb254_leaf_hash_rows_dev(pb254_ctx* ctx, const uint64_t* d_matrix, size_t stride, size_t cols, size_t rows,
+                             uint64_t* d_digests_out);
+/* 2^log_roots roots of the subtree over tree positions [first, first + 2^log_sub) of a tree with 2^log_total
+ * leaves, leaf(q) = d_all_digests[bit_reverse(q)] (digests of all rows in natural row order). */
+int pb254_merkle_subtree_dev(pb254_ctx* ctx, const uint64_t* d_all_digests, uint32_t log_total, size_t first,
+                             uint32_t log_sub, uint32_t log_roots, uint64_t* d_roots_out);
+
 /* ---- trace generation (K1 + K2) -------------------------------------------------------------- */
 /* generate_trace(&inputs, min_rows): fills cols_out, column-major pb254_trace_width(kind) x
  * pb254_trace_rows(n_inputs, min_rows), with the bit-exact trace of the reference. min_rows must make

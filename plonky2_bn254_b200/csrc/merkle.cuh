@@ -21,6 +21,7 @@ struct LeafHashK {
   size_t stride;
   int W, log_n;
   Digest* out;
+  int natural = 0;  // 1: digest of row j is stored at j (row-sharded hashing), 0: at bit_reverse(j)
   PB_HD void operator()(size_t j) const {
     u64 s[12];
 #pragma unroll
@@ -42,7 +43,7 @@ struct LeafHashK {
     Digest d;
 #pragma unroll
     for (int i = 0; i < 4; i++) d.e[i] = s[i];
-    out[gl::brev32((u32)j, log_n)] = d;
+    out[natural ? j : (size_t)gl::brev32((u32)j, log_n)] = d;
   }
 };
 
@@ -86,11 +87,11 @@ __device__ __forceinline__ void stage_rc2(u64* rc2) {
 
 // one thread per LDE row
 __global__ void __launch_bounds__(128, 6) k_leaf_hash(const u64* __restrict__ lde, size_t stride, int W, int log_n,
-                                                   Digest* __restrict__ out) {
+                                                   Digest* __restrict__ out, size_t rows, int natural) {
   __shared__ __align__(16) u64 rc2[poseidon::RC2_WORDS];
   stage_rc2(rc2);
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ((size_t)1 << log_n)) return;
+  if (j >= rows) return;
   const u64* p = lde + j;
   u64 s[12];
 #pragma unroll
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(128, 6) k_leaf_hash(const u64* __restrict__ ld
   Digest d;
 #pragma unroll
   for (int i = 0; i < 4; i++) d.e[i] = s[i];
-  out[gl::brev32((u32)j, log_n)] = d;
+  out[natural ? j : (size_t)gl::brev32((u32)j, log_n)] = d;
 }
 
 __global__ void __launch_bounds__(128, 6) k_level(const Digest* __restrict__ child, Digest* __restrict__ parent, size_t n) {
@@ -176,7 +177,7 @@ static inline void build_from_lde(const u64* lde, size_t stride, int W, int log_
     pb_launch("leaf copy", k, (size_t)1 << log_n, s, 128);
   } else {
     const size_t n = (size_t)1 << log_n;
-    k_leaf_hash<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(lde, stride, W, log_n, digests);
+    k_leaf_hash<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(lde, stride, W, log_n, digests, n, 0);
     g_pb_launches++;
     pb_check_last("leaf hash");
   }
@@ -188,5 +189,32 @@ static inline void build_from_rows(const u64* rows, int len, int log_n, int cap_
   pb_launch("row hash", k, (size_t)1 << log_n, s, 128);
   build_levels(digests, log_n, cap_height, s);
 }
+
+
+// ---- row-sharded pieces for the oversized-trace mode -------------------------------------
+// digests of `rows` rows of a column-major matrix [W][stride], natural order: out[i] = H(row i)
+static inline void hash_rows_natural(const u64* m, size_t stride, int W, size_t rows, Digest* out, pbStream s) {
+#if PB_HOSTSIM
+  LeafHashK k{m, stride, W, 0, out, 1};
+  pb_launch("leaf hash (rows)", k, rows, s, 128);
+#else
+  if (W <= 4) {
+    LeafHashK k{m, stride, W, 0, out, 1};
+    pb_launch("leaf copy (rows)", k, rows, s, 128);
+  } else {
+    k_leaf_hash<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(m, stride, W, 0, out, rows, 1);
+    g_pb_launches++;
+    pb_check_last("leaf hash (rows)");
+  }
+#endif
+}
+// leaves[q] = all[bit_reverse(first + q, log_N)] for q < 2^log_sub: the leaves of one subtree in tree order
+struct SubtreeLeavesK {
+  const Digest* all;
+  Digest* leaves;
+  size_t first;
+  int log_N;
+  PB_HD void operator()(size_t q) const { leaves[q] = all[gl::brev32((u32)(first + q), log_N)]; }
+};
 
 }  // namespace merkle

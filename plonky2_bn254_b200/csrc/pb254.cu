@@ -334,6 +334,63 @@ int pb254_prove_trace(pb254_ctx* c, int kind, const uint64_t* trace_cols, size_t
   });
 }
 
+// ---- device-pointer building blocks of the oversized-trace mode (column-sharded LDE -> all-to-all ->
+// row-sharded leaf hashing -> digest all-gather -> per-rank subtree), orchestrated by plonky2_bn254_b200/dist.py
+int pb254_lde_dev(pb254_ctx* c, const uint64_t* d_values, size_t cols, size_t n, uint32_t rate_bits, int from_coeffs,
+                  uint64_t* d_lde_out) {
+  return guarded([&] {
+    pb_set_device(c->device);
+    int L = ilog2_strict(n);
+    c->arena.reserve(cols * n * 8 + 4096);
+    c->arena.reset();
+    u64* scratch = c->arena.alloc_n<u64>(cols * n);
+    c->times.clear();
+    int t0 = c->times.begin("lde", c->stream);
+    ntt::lde_columns(c->tables, d_values, n, d_lde_out, n << rate_bits, scratch, (int)cols, L, (int)rate_bits,
+                     from_coeffs ? ntt::FROM_COEFFS_LDE : ntt::FROM_VALUES_LDE, c->stream);
+    c->times.end(t0, c->stream);
+    pb_sync(c->stream);
+    c->times.resolve();
+  });
+}
+
+int pb254_leaf_hash_rows_dev(pb254_ctx* c, const uint64_t* d_matrix, size_t stride, size_t cols, size_t rows,
+                             uint64_t* d_digests_out) {
+  return guarded([&] {
+    pb_set_device(c->device);
+    c->times.clear();
+    int t0 = c->times.begin("leaf hash rows", c->stream);
+    merkle::hash_rows_natural(d_matrix, stride, (int)cols, rows, (merkle::Digest*)d_digests_out, c->stream);
+    c->times.end(t0, c->stream);
+    pb_sync(c->stream);
+    c->times.resolve();
+  });
+}
+
+// Roots at height `log_sub - log_roots` of the subtree whose leaves are tree positions [first, first + 2^log_sub):
+// leaf(q) = d_all_digests[bit_reverse(q, log_total)] (digests of all rows in natural row order).
+int pb254_merkle_subtree_dev(pb254_ctx* c, const uint64_t* d_all_digests, uint32_t log_total, size_t first,
+                             uint32_t log_sub, uint32_t log_roots, uint64_t* d_roots_out) {
+  return guarded([&] {
+    pb_set_device(c->device);
+    if (log_roots > log_sub || log_sub > log_total) throw Pb254Error(PB254_E_BAD_ARG, "subtree shape");
+    size_t nd = merkle::tree_digests((int)log_sub, (int)log_roots);
+    c->arena.reserve(nd * 32 + 4096);
+    c->arena.reset();
+    merkle::Digest* dig = c->arena.alloc_n<merkle::Digest>(nd);
+    c->times.clear();
+    int t0 = c->times.begin("subtree", c->stream);
+    pb_launch("subtree leaves", merkle::SubtreeLeavesK{(const merkle::Digest*)d_all_digests, dig, first, (int)log_total},
+              (size_t)1 << log_sub, c->stream, 128);
+    merkle::build_levels(dig, (int)log_sub, (int)log_roots, c->stream);
+    size_t nr = (size_t)1 << log_roots;
+    pb_d2d(d_roots_out, dig + (nd - nr), nr * 32, c->stream);
+    c->times.end(t0, c->stream);
+    pb_sync(c->stream);
+    c->times.resolve();
+  });
+}
+
 // verify(stark, config, ctls, proof, [], extra_looking_values) of src/starks/common/verifier.rs:32-98, with the
 // extra looking values recomputed natively from the batch as run_once does (g1/scalar_mul_ctl.rs:57-80).
 int pb254_verify(const uint64_t* proof_words, size_t n_words, const uint64_t* inputs, const uint64_t* timestamps,

@@ -65,3 +65,87 @@ def max_over_ranks(dist, seconds: float, device=None) -> float:
     t = torch.tensor([seconds], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- oversized single trace: column-sharded LDE -> all-to-all -> row-sharded Merkle -------------
+def shard_columns(total_cols: int, world: int):
+    """Contiguous column ranges in rank order; [(first, count)] per rank."""
+    return [(total_cols * g // world, total_cols * (g + 1) // world - total_cols * g // world) for g in range(world)]
+
+
+def dist_commit(ctx, dist, shard, total_cols: int, rate_bits: int, cap_height: int, timings: dict | None = None):
+    """PolynomialBatch::from_values of ONE matrix spread over `world` ranks; returns the Merkle cap
+    (2^cap_height x 4, torch int64 tensor on the shard's device), identical on every rank and identical to the
+    single-GPU commitment.
+
+    `shard`: this rank's columns as a contiguous torch.int64 tensor [cols_g, n] (canonical field elements) on
+    the context's device, column ranges as given by `shard_columns`. `dist` is torch.distributed (NCCL on GPUs,
+    gloo in the CPU tests) or None for a single rank.
+
+      A  LDE of the local columns (pb254_lde_dev), no communication
+      B  ONE all-to-all: rank h receives the row block [h N/G, (h+1) N/G) of every column
+      C  row-local leaf hashing (pb254_leaf_hash_rows_dev), digests in natural row order
+      D  all-gather of the 32-byte digests (N x 32 B)
+      E  every rank builds the subtree under its own cap entries (pb254_merkle_subtree_dev); all-gather of the cap
+    """
+    import time
+    import torch
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    cols_g, n = shard.shape
+    N = n << rate_bits
+    log_N = N.bit_length() - 1
+    log_g = world.bit_length() - 1
+    assert (1 << log_g) == world and world <= (1 << cap_height) and N % world == 0
+    assert shard.dtype == torch.int64 and shard.is_contiguous()
+    counts = [c for _, c in shard_columns(total_cols, world)]
+    assert counts[rank] == cols_g
+    rows = N // world
+    dev = shard.device
+    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
+    t = {}
+
+    def mark(name, t0):
+        sync()
+        t[name] = (time.perf_counter() - t0) * 1e3
+
+    t0 = time.perf_counter()
+    lde = torch.empty((cols_g, N), dtype=torch.int64, device=dev)
+    ctx.lde_dev(shard.data_ptr(), cols_g, n, rate_bits, lde.data_ptr())
+    mark("lde (column shard)", t0)
+    t0 = time.perf_counter()
+    if world > 1:
+        send = lde.view(cols_g, world, rows).permute(1, 0, 2).contiguous()  # [peer][col][row block]
+        del lde
+        recv = torch.empty((total_cols, rows), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv.view(-1), send.view(-1), output_split_sizes=[c * rows for c in counts],
+                               input_split_sizes=[cols_g * rows] * world)
+        del send
+    else:
+        recv = lde
+    mark("all-to-all (columns -> row blocks)", t0)
+    t0 = time.perf_counter()
+    dig = torch.empty((rows, 4), dtype=torch.int64, device=dev)
+    ctx.leaf_hash_rows_dev(recv.data_ptr(), rows, total_cols, rows, dig.data_ptr())
+    mark("leaf hash (row block)", t0)
+    t0 = time.perf_counter()
+    if world > 1:
+        all_dig = torch.empty((N, 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_dig, dig)
+    else:
+        all_dig = dig
+    mark("all-gather digests", t0)
+    t0 = time.perf_counter()
+    log_roots = cap_height - log_g
+    roots = torch.empty((1 << log_roots, 4), dtype=torch.int64, device=dev)
+    ctx.merkle_subtree_dev(all_dig.data_ptr(), log_N, rank << (log_N - log_g), log_N - log_g, log_roots,
+                           roots.data_ptr())
+    if world > 1:
+        cap = torch.empty((1 << cap_height, 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(cap, roots)
+    else:
+        cap = roots
+    mark("subtree + cap all-gather", t0)
+    if timings is not None:
+        timings.update(t)
+    return cap

@@ -180,6 +180,21 @@ class Context:
                                              C.c_uint32(cap_height), C.c_int(int(from_coeffs)), _p(cap), _p(dig)))
         return (cap, dig) if want_digests else cap
 
+    # ---- device-pointer building blocks (oversized-trace mode, see dist.py) ---------------------
+    def lde_dev(self, d_values: int, cols: int, n: int, rate_bits: int, d_out: int, from_coeffs=False):
+        self.L.check(self.L.lib.pb254_lde_dev(self._h, C.c_void_p(d_values), C.c_size_t(cols), C.c_size_t(n),
+                                              C.c_uint32(rate_bits), C.c_int(int(from_coeffs)), C.c_void_p(d_out)))
+
+    def leaf_hash_rows_dev(self, d_matrix: int, stride: int, cols: int, rows: int, d_digests: int):
+        self.L.check(self.L.lib.pb254_leaf_hash_rows_dev(self._h, C.c_void_p(d_matrix), C.c_size_t(stride),
+                                                         C.c_size_t(cols), C.c_size_t(rows), C.c_void_p(d_digests)))
+
+    def merkle_subtree_dev(self, d_all_digests: int, log_total: int, first: int, log_sub: int, log_roots: int,
+                           d_roots: int):
+        self.L.check(self.L.lib.pb254_merkle_subtree_dev(self._h, C.c_void_p(d_all_digests), C.c_uint32(log_total),
+                                                         C.c_size_t(first), C.c_uint32(log_sub),
+                                                         C.c_uint32(log_roots), C.c_void_p(d_roots)))
+
     # ---- trace generation -----------------------------------------------------------------
     def generate_trace(self, kind, inputs, timestamps, min_rows=1 << 16):
         inputs = _u64(inputs)

@@ -69,3 +69,49 @@ def test_two_rank_replicas(oracle):
         inp, ts = D.make_batch(I.KIND_FQ, 1, 9, b)
         pf, _, _ = oracle.prove_inputs(I.KIND_FQ, inp, ts)
         assert D.proof_digest(pf.words()).hex() == res[0][2][b]
+
+
+def _commit_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from plonky2_bn254_b200 import build, dist as D, ffi
+    from util import rand_field
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = ffi.Context(0, library=ffi.Library(build.HOSTSIM_LIB))
+    rng = np.random.default_rng(77)
+    full = rand_field(rng, (21, 1 << 9))            # every rank regenerates the same matrix, keeps its columns
+    first, cnt = D.shard_columns(21, world)[rank]
+    shard = torch.from_numpy(full[first:first + cnt].view(np.int64).copy())
+    cap = D.dist_commit(ctx, dist if world > 1 else None, shard, 21, 1, 4)
+    q.put((rank, cap.numpy().view(np.uint64).tolist()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_dist_commit_matches_single_commit(oracle, world):
+    """Column-sharded LDE -> all-to-all -> row-sharded leaf hashing -> digest all-gather -> per-rank subtrees gives
+    the same Merkle cap as PolynomialBatch::from_values on one device (oracle), for 1, 2 and 4 ranks (gloo; the
+    prover context is the hostsim build, whose 'device pointers' are host pointers)."""
+    from plonky2_bn254_b200 import build
+    from util import rand_field
+    build.build_hostsim()
+    port = _free_port()
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    procs = [ctxmp.Process(target=_commit_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(77)
+    full = rand_field(rng, (21, 1 << 9))
+    want = oracle.commit(full, 1, 4).tolist()
+    for _, cap in res:
+        assert cap == want
