@@ -286,4 +286,31 @@ PB_HD Jac<F> jac_add_mixed(const Jac<F>& p, const Aff<F>& q, int& status) {
   return r;
 }
 
+
+// complete addition of two Jacobian points; Z = 0 encodes the point at infinity
+template <class F>
+PB_HD Jac<F> jac_add_complete(const Jac<F>& p, const Jac<F>& q) {
+  typedef typename F::T T;
+  if (F::is_zero(p.Z)) return q;
+  if (F::is_zero(q.Z)) return p;
+  T Z1Z1 = F::sqr(p.Z), Z2Z2 = F::sqr(q.Z);
+  T U1 = F::mul(p.X, Z2Z2), U2 = F::mul(q.X, Z1Z1);
+  T S1 = F::mul(p.Y, F::mul(q.Z, Z2Z2)), S2 = F::mul(q.Y, F::mul(p.Z, Z1Z1));
+  T H = F::sub(U2, U1), rr = F::sub(S2, S1);
+  if (F::is_zero(H)) {
+    if (F::is_zero(rr)) return jac_double<F>(p);  // a point of order two doubles to Z = 0
+    Jac<F> inf;
+    inf.X = F::one();
+    inf.Y = F::one();
+    inf.Z = F::zero();
+    return inf;
+  }
+  T HH = F::sqr(H), HHH = F::mul(H, HH), V = F::mul(U1, HH);
+  Jac<F> r;
+  r.X = F::sub(F::sub(F::sqr(rr), HHH), F::dbl(V));
+  r.Y = F::sub(F::mul(rr, F::sub(V, r.X)), F::mul(S1, HHH));
+  r.Z = F::mul(F::mul(p.Z, q.Z), H);
+  return r;
+}
+
 }  // namespace bn

@@ -288,6 +288,141 @@ struct ChainsK {
   }
 };
 
+#if !PB_HOSTSIM
+// ---- the same chains with instance- AND step-level parallelism (device build) -----------------------------
+// ChainsK walks both 256-step chains of an instance in one thread: with 2^10 instances that is 32 warps on a
+// 148-SM machine, purely latency-bound (9.6 ms for G1, 48 ms for G2). Only the doubling chain is inherently
+// sequential. The running sums S_j = offset + sum_{i <= j, bit_i} D_i are a prefix sum in the curve group, so
+// they are computed by a 256-thread block per instance with an 8-step scan of complete Jacobian additions; the
+// row values T_j = S_(j-1) + D_j are then one mixed addition per thread - the reference's own addition, with
+// its status checks - and every Jacobian -> affine conversion is an independent Fermat inversion per thread.
+// Affine coordinates are unique, so the trace is bit-identical to the sequential walk.
+template <class F>
+__global__ void __launch_bounds__(32) k_dbl_chain(CurveBufs<F> B, const u64* __restrict__ inputs, int in_words, size_t K) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const u64* w = inputs + k * in_words;
+  const int FW = FieldIO<F>::WORDS;
+  bn::Aff<F> x, off;
+  bool ok = FieldIO<F>::load(w + 4, x.x) & FieldIO<F>::load(w + 4 + FW, x.y) &
+            FieldIO<F>::load(w + 4 + 2 * FW, off.x) & FieldIO<F>::load(w + 4 + 3 * FW, off.y);
+  if (!ok) {
+    set_err(B.err, ERR_NOT_CANONICAL);
+    x.x = x.y = off.x = off.y = F::one();  // keep the later kernels well defined; the error word wins
+  }
+  B.D[k] = x;
+  B.off[k] = off;
+  bn::Jac<F> p;
+  p.X = x.x;
+  p.Y = x.y;
+  p.Z = F::one();
+  for (int j = 0; j < 256; j++) {
+    if (F::is_zero(p.Y)) set_err(B.err, ERR_INFINITY);  // 2-torsion: doubling gives infinity
+    p = bn::jac_double<F>(p);
+    B.tmp[(size_t)j * K + k] = p;
+  }
+}
+
+// dst[dst_off + i] = affine(src[i]); one thread per AFF_CH consecutive points sharing one Fermat inversion
+// (Montgomery's trick): 3 multiplications per point for the inverse instead of ~380
+static constexpr int AFF_CH = 16;
+template <class F>
+__global__ void __launch_bounds__(128) k_to_affine(const bn::Jac<F>* __restrict__ src, bn::Aff<F>* __restrict__ dst,
+                                                   size_t count, size_t dst_off, int* err) {
+  typedef typename F::T T;
+  const size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * AFF_CH;
+  if (base >= count) return;
+  const int cnt = (int)(count - base < (size_t)AFF_CH ? count - base : (size_t)AFF_CH);
+  T pref[AFF_CH];
+  T acc = F::one();
+  for (int i = 0; i < cnt; i++) {
+    T z = src[base + i].Z;
+    if (F::is_zero(z)) {  // only after an error was flagged upstream
+      set_err(err, ERR_INFINITY);
+      z = F::one();
+    }
+    pref[i] = acc;
+    acc = F::mul(acc, z);
+  }
+  T inv = F::inv(acc);
+  for (int i = cnt - 1; i >= 0; i--) {
+    const bn::Jac<F> p = src[base + i];
+    const T z = F::is_zero(p.Z) ? F::one() : p.Z;
+    const T zi = F::mul(inv, pref[i]);
+    inv = F::mul(inv, z);
+    const T zi2 = F::sqr(zi);
+    bn::Aff<F> a;
+    a.x = F::mul(p.X, zi2);
+    a.y = F::mul(p.Y, F::mul(zi, zi2));
+    dst[dst_off + base + i] = a;
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_sum_scan(CurveBufs<F> B, bn::Jac<F>* __restrict__ ping, bn::Jac<F>* __restrict__ pong,
+                                                  const u64* __restrict__ inputs, int in_words, size_t K) {
+  const size_t k = blockIdx.x;
+  const int j = threadIdx.x;  // 0..255
+  const u64* w = inputs + k * in_words;
+  const bool bit = scalar_bit(w, j);
+  bn::Jac<F> e;
+  if (bit) {
+    const bn::Aff<F> d = B.D[(size_t)j * K + k];
+    e.X = d.x;
+    e.Y = d.y;
+    e.Z = F::one();
+  } else {
+    e.X = F::one();
+    e.Y = F::one();
+    e.Z = F::zero();
+  }
+  // inclusive Hillis-Steele scan over the 256 steps of this instance (global ping-pong buffers, [j][K] layout)
+  bn::Jac<F>* cur = ping;
+  bn::Jac<F>* nxt = pong;
+  cur[(size_t)j * K + k] = e;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    bn::Jac<F> v = cur[(size_t)j * K + k];
+    if (j >= d) v = bn::jac_add_complete<F>(cur[(size_t)(j - d) * K + k], v);
+    nxt[(size_t)j * K + k] = v;
+    __syncthreads();
+    bn::Jac<F>* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  // S_(j-1) = offset + P_(j-1)
+  const bn::Aff<F> off = B.off[k];
+  bn::Jac<F> sprev;
+  sprev.X = off.x;
+  sprev.Y = off.y;
+  sprev.Z = F::one();
+  if (j > 0) sprev = bn::jac_add_complete<F>(cur[(size_t)(j - 1) * K + k], sprev);
+  if (F::is_zero(sprev.Z)) {  // an earlier row produced the point at infinity (flagged there as well)
+    set_err(B.err, ERR_INFINITY);
+    sprev.X = off.x;
+    sprev.Y = off.y;
+    sprev.Z = F::one();
+  }
+  int st;
+  bn::Jac<F> t = bn::jac_add_mixed<F>(sprev, B.D[(size_t)j * K + k], st);
+  if (st == 2) {
+    set_err(B.err, ERR_INFINITY);
+    t = sprev;
+  }
+  if (st == 1 && F::is_zero(sprev.Y)) set_err(B.err, ERR_INFINITY);
+  __syncthreads();  // everyone has read the scan result before it is overwritten with T
+  nxt[(size_t)j * K + k] = t;  // Jacobian T_j; k_to_affine turns it into B.T
+  // index of the T that gives S_j: the last set bit at or below j, or -1 (the offset)
+  int last = -1;
+  for (int wi = j >> 6; wi >= 0 && last < 0; wi--) {
+    u64 m = w[wi];
+    if (wi == (j >> 6) && (j & 63) != 63) m &= (((u64)2) << (j & 63)) - 1;
+    if (m) last = wi * 64 + 63 - __clzll((long long)m);
+  }
+  B.sidx[(size_t)j * K + k] = (short)last;
+}
+#endif
+
 // operands of row r of instance k
 template <class F>
 PB_HD void row_operands(const CurveBufs<F>& B, size_t k, size_t K, int r, bn::Aff<F>& a, bn::Aff<F>& b) {
@@ -818,7 +953,20 @@ static inline void run_curve(Arena& ar, const Layout& l, const u64* d_inputs, co
   const int nden = FieldIO<F>::NDEN;
   B.den = ar.alloc_n<bn::Fq>((size_t)nden * PERIOD * K);
   B.err = d_err;
+#if PB_HOSTSIM
   pb_launch("tracegen chains", ChainsK<F>{B, d_inputs, l.in_words, K}, K, s, 32);
+#else
+  {
+    bn::Jac<F>* pong = ar.alloc_n<bn::Jac<F>>(256 * K);
+    k_dbl_chain<F><<<(unsigned)((K + 31) / 32), 32, 0, s>>>(B, d_inputs, l.in_words, K);
+    k_to_affine<F><<<(unsigned)((256 * K / AFF_CH + 127) / 128), 128, 0, s>>>(B.tmp, B.D, 256 * K, K, d_err);
+    // ping = B.tmp (free again), pong: the scan ends in ping after 8 swaps and the Jacobian T_j land in pong
+    k_sum_scan<F><<<(unsigned)K, 256, 0, s>>>(B, B.tmp, pong, d_inputs, l.in_words, K);
+    k_to_affine<F><<<(unsigned)((256 * K / AFF_CH + 127) / 128), 128, 0, s>>>(pong, B.T, 256 * K, 0, d_err);
+    g_pb_launches += 4;
+    pb_check_last("tracegen chains");
+  }
+#endif
   pb_launch("tracegen dens", DensK<F>{B, K}, K * PERIOD, s, 128);
   size_t nd = (size_t)nden * PERIOD * K;
   pb_launch("tracegen batchinv", BatchInvK{B.den, nd}, (nd + 15) / 16, s, 64);

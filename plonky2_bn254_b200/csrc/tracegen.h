@@ -68,7 +68,7 @@ static inline size_t scratch_bytes(int kind, size_t K) {
   if (kind == 2) return (257 + 256) * K * 32 + 256 * K * 2 + PERIOD * 5 * 8 + 8192;
   size_t aff = 2 * fe, jac = 3 * fe;
   size_t nden = kind == 1 ? 3 : 1;
-  return (257 + 256 + 1) * K * aff + 256 * K * jac + 256 * K * fe + 256 * K * 2 + nden * PERIOD * K * 32 +
+  return (257 + 256 + 1) * K * aff + 2 * 256 * K * jac + 256 * K * fe + 256 * K * 2 + nden * PERIOD * K * 32 +
          PERIOD * 5 * 8 + 16384;
 }
 
