@@ -210,6 +210,20 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     pb_h2d(d_w, w.data(), w.size() * 8, s);
     pb_sync(s);
   }
+  const int bpow_stride = 2 * l.L + 17;
+  u64* d_bpow = ar.alloc_n<u64>((size_t)nch * bpow_stride);
+  {
+    std::vector<u64> bp((size_t)nch * bpow_stride);
+    for (int j = 0; j < nch; j++) {
+      u64 pw = 1;
+      for (int k = 0; k < bpow_stride; k++) {
+        bp[(size_t)j * bpow_stride + k] = pw;
+        pw = gl::mul(pw, chal.beta[j]);
+      }
+    }
+    pb_h2d(d_bpow, bp.data(), bp.size() * 8, s);
+    pb_sync(s);
+  }
   u64* qvals = ar.alloc_n<u64>((size_t)nch * qsize);
   u64* qcoef = ar.alloc_n<u64>((size_t)nch * qsize);
   int* d_err = ar.alloc_n<int>(1);
@@ -224,6 +238,8 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     qp.ax_stride = N;
     qp.out = qvals;
     qp.weights = d_w;
+    qp.bpow = d_bpow;
+    qp.bpow_stride = bpow_stride;
     qp.size = qsize;
     qp.log_size = L + 1;
     qp.step = (size_t)1 << (r - 1);

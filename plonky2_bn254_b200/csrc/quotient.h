@@ -12,6 +12,8 @@ struct Params {
   size_t ax_stride;
   u64* out;           // nch x size, natural order: combined constraints / Z_H at 7 * w^i
   const u64* weights; // [K][nch]: alpha_j^(K-1-k)
+  const u64* bpow;    // [nch][bpow_stride]: beta_j^k, k < 2 L + 17 (CTL combinations)
+  int bpow_stride;
   size_t size;        // quotient domain size = 2 n
   int log_size;
   size_t step;        // LDE index of quotient point i is i * step  (2^(rate_bits - 1))

@@ -36,6 +36,33 @@ struct LY {
   static constexpr int BASE_CONSTRAINTS = KIND == 0 ? 1111 : KIND == 1 ? 1693 : 770;
 };
 
+// Arithmetic inside the kernel works on lazy u64 representatives on the device (any u64 congruent to the value;
+// gl::mul_lazy / add_lazy / sub_lazy and the 160-bit accumulator accept and produce them) and on canonical values
+// in the host build; results are made canonical where a constraint group is closed (Emit::end_group).
+PB_HD u64 q_add(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return gl::add_lazy(a, b);
+#else
+  return gl::add(a % gl::P, b % gl::P);
+#endif
+}
+PB_HD u64 q_sub(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return gl::sub_lazy(a, b);
+#else
+  return gl::sub(a % gl::P, b % gl::P);
+#endif
+}
+PB_HD u64 q_mul(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return gl::mul_lazy(a, b);
+#else
+  return gl::mul(a % gl::P, b % gl::P);
+#endif
+}
+PB_HD u64 q_dbl(u64 a) { return q_add(a, a); }
+PB_HD u64 q_sqr(u64 a) { return q_mul(a, a); }
+
 struct Emit {
   const u64* w;
   int nch, k;
@@ -92,11 +119,11 @@ Q_NOINLINE void mz_values(const u64* tr, size_t stride, size_t i0, const u64* in
   const u64 P16[16] = TG_P16_U64;
   const u64* col = tr + (size_t)auxcol * stride + i0;
   u64 s = col[0];
-  out33[0] = gl::sub(gl::sqr(s), s);
-  u64 sign = gl::sub(gl::dbl(s), 1);
+  out33[0] = q_sub(q_sqr(s), s);
+  u64 sign = q_sub(q_dbl(s), 1);
   u64 q[17];
 #pragma unroll 1
-  for (int i = 0; i < 17; i++) q[i] = gl::mul(sign, col[(size_t)(1 + i) * stride]);
+  for (int i = 0; i < 17; i++) q[i] = q_mul(sign, col[(size_t)(1 + i) * stride]);
   const u64 base = (u64)1 << 16, offset = (u64)1 << 29;
   u64 ap_prev = 0;
 #pragma unroll 1
@@ -108,10 +135,10 @@ Q_NOINLINE void mz_values(const u64* tr, size_t stride, size_t i0, const u64* in
     u64 c = s2.reduce();
     u64 ap = 0;
     if (k < 31)
-      ap = gl::add(gl::sub(col[(size_t)(18 + k) * stride], offset), gl::mul(base, col[(size_t)(49 + k) * stride]));
+      ap = q_add(q_sub(col[(size_t)(18 + k) * stride], offset), q_mul(base, col[(size_t)(49 + k) * stride]));
     // (x - base) * ap(x): coefficient k is ap[k-1] - base * ap[k]
-    c = gl::add(c, gl::sub(ap_prev, gl::mul(base, ap)));
-    if (k < 31) c = gl::sub(c, in[k]);
+    c = q_add(c, q_sub(ap_prev, q_mul(base, ap)));
+    if (k < 31) c = q_sub(c, in[k]);
     out33[1 + k] = c;
     ap_prev = ap;
   }
@@ -145,15 +172,15 @@ struct QuotientK {
     u64 *dx = S.u0, *iv = S.u1, *in = S.c0;
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      dx[i] = gl::sub(TL(i0, col_b + i), TL(i0, col_a + i));
+      dx[i] = q_sub(TL(i0, col_b + i), TL(i0, col_a + i));
       iv[i] = TL(i0, auxcol + i);
     }
     conv31(dx, iv, in);
     u64 is_zero = TL(i0, is_zero_col);
-    in[0] = gl::add(in[0], gl::sub(is_zero, 1));
+    in[0] = q_add(in[0], q_sub(is_zero, 1));
     mz(E, S, i0, in, auxcol + 16);
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) E.term(gl::mul(dx[i], is_zero));
+    for (int i = 0; i < 16; i++) E.term(q_mul(dx[i], is_zero));
   }
 
   PB_HD void ld16(size_t i0, int col, u64 out[16]) const {
@@ -166,41 +193,41 @@ struct QuotientK {
     imz(E, S, i0, b, a, A, A + 1);
     E.end_group(filter);
     u64 is_x_eq = TL(i0, A), is_x_eq_filter = TL(i0, A + 97);
-    E.term(gl::sub(gl::mul(filter, is_x_eq), is_x_eq_filter));
+    E.term(q_sub(q_mul(filter, is_x_eq), is_x_eq_filter));
     E.end_group(1);
     u64 *lam = S.l0, *t0 = S.u0, *in = S.c0, *in2 = S.d0;
     ld16(i0, A + 98, lam);
     // a.x != b.x : lambda * dx - (b.y - a.y)
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) t0[i] = gl::sub(TL(i0, b + i), TL(i0, a + i));
+    for (int i = 0; i < 16; i++) t0[i] = q_sub(TL(i0, b + i), TL(i0, a + i));
     conv31(lam, t0, in);
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) in[i] = gl::sub(in[i], gl::sub(TL(i0, b + 16 + i), TL(i0, a + 16 + i)));
+    for (int i = 0; i < 16; i++) in[i] = q_sub(in[i], q_sub(TL(i0, b + 16 + i), TL(i0, a + 16 + i)));
     mz(E, S, i0, in, A + 114);
-    E.end_group(gl::sub(filter, is_x_eq_filter));
+    E.end_group(q_sub(filter, is_x_eq_filter));
     // a.x == b.x : 2 lambda a.y - 3 a.x^2
     ld16(i0, a, t0);
     conv31(t0, t0, in2);
     ld16(i0, a + 16, t0);
     conv31(lam, t0, in);
 #pragma unroll 1
-    for (int i = 0; i < 31; i++) in[i] = gl::sub(gl::dbl(in[i]), gl::add(gl::dbl(in2[i]), in2[i]));
+    for (int i = 0; i < 31; i++) in[i] = q_sub(q_dbl(in[i]), q_add(q_dbl(in2[i]), in2[i]));
     mz(E, S, i0, in, A + 114);
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) E.term(gl::sub(TL(i0, a + 16 + i), TL(i0, b + 16 + i)));
+    for (int i = 0; i < 16; i++) E.term(q_sub(TL(i0, a + 16 + i), TL(i0, b + 16 + i)));
     E.end_group(is_x_eq_filter);
     // x : lambda^2 - (a.x + b.x + c.x)
     conv31(lam, lam, in);
 #pragma unroll 1
     for (int i = 0; i < 16; i++)
-      in[i] = gl::sub(in[i], gl::add(gl::add(TL(i0, a + i), TL(i0, b + i)), TL(i0, c + i)));
+      in[i] = q_sub(in[i], q_add(q_add(TL(i0, a + i), TL(i0, b + i)), TL(i0, c + i)));
     mz(E, S, i0, in, A + 194);
     // y : lambda (c.x - a.x) + c.y + a.y
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) t0[i] = gl::sub(TL(i0, c + i), TL(i0, a + i));
+    for (int i = 0; i < 16; i++) t0[i] = q_sub(TL(i0, c + i), TL(i0, a + i));
     conv31(lam, t0, in);
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) in[i] = gl::add(in[i], gl::add(TL(i0, c + 16 + i), TL(i0, a + 16 + i)));
+    for (int i = 0; i < 16; i++) in[i] = q_add(in[i], q_add(TL(i0, c + 16 + i), TL(i0, a + 16 + i)));
     mz(E, S, i0, in, A + 274);
     E.end_group(filter);
   }
@@ -212,22 +239,22 @@ struct QuotientK {
     conv31(x0, y0, c0);
     conv31(x1, y1, t);
 #pragma unroll 1
-    for (int i = 0; i < 31; i++) c0[i] = gl::sub(c0[i], t[i]);
+    for (int i = 0; i < 31; i++) c0[i] = q_sub(c0[i], t[i]);
     conv31(x0, y1, c1);
     conv31(x1, y0, t);
 #pragma unroll 1
-    for (int i = 0; i < 31; i++) c1[i] = gl::add(c1[i], t[i]);
+    for (int i = 0; i < 31; i++) c1[i] = q_add(c1[i], t[i]);
   }
 
   PB_HD void add_g2(Emit& E, Scratch& S, size_t i0, u64 filter) const {
     const int A = Y::aux, a = Y::a, b = Y::b, c = Y::c;  // points: x.c0 | x.c1 | y.c0 | y.c1
     u64 is_x_eq = TL(i0, A), z0 = TL(i0, A + 1), z1 = TL(i0, A + 2);
-    E.term(gl::sub(gl::mul(z0, z1), is_x_eq));
+    E.term(q_sub(q_mul(z0, z1), is_x_eq));
     imz(E, S, i0, b, a, A + 1, A + 3);
     imz(E, S, i0, b + 16, a + 16, A + 2, A + 99);
     E.end_group(filter);
     u64 is_x_eq_filter = TL(i0, A + 195);
-    E.term(gl::sub(gl::mul(filter, is_x_eq), is_x_eq_filter));
+    E.term(q_sub(q_mul(filter, is_x_eq), is_x_eq_filter));
     E.end_group(1);
     u64 *l0 = S.l0, *l1 = S.l1, *u0 = S.u0, *u1 = S.u1, *c0 = S.c0, *c1 = S.c1, *d0 = S.d0, *d1 = S.d1;
     ld16(i0, A + 196, l0);
@@ -235,18 +262,18 @@ struct QuotientK {
     // lambda * dx - dy
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      u0[i] = gl::sub(TL(i0, b + i), TL(i0, a + i));
-      u1[i] = gl::sub(TL(i0, b + 16 + i), TL(i0, a + 16 + i));
+      u0[i] = q_sub(TL(i0, b + i), TL(i0, a + i));
+      u1[i] = q_sub(TL(i0, b + 16 + i), TL(i0, a + 16 + i));
     }
     ext_conv(S, l0, l1, u0, u1, c0, c1);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      c0[i] = gl::sub(c0[i], gl::sub(TL(i0, b + 32 + i), TL(i0, a + 32 + i)));
-      c1[i] = gl::sub(c1[i], gl::sub(TL(i0, b + 48 + i), TL(i0, a + 48 + i)));
+      c0[i] = q_sub(c0[i], q_sub(TL(i0, b + 32 + i), TL(i0, a + 32 + i)));
+      c1[i] = q_sub(c1[i], q_sub(TL(i0, b + 48 + i), TL(i0, a + 48 + i)));
     }
     mz(E, S, i0, c0, A + 228);
     mz(E, S, i0, c1, A + 308);
-    E.end_group(gl::sub(filter, is_x_eq_filter));
+    E.end_group(q_sub(filter, is_x_eq_filter));
     // 2 lambda a.y - 3 a.x^2
     {
       ld16(i0, a, u0);
@@ -257,35 +284,35 @@ struct QuotientK {
       ext_conv(S, l0, l1, u0, u1, c0, c1);
 #pragma unroll 1
       for (int i = 0; i < 31; i++) {
-        c0[i] = gl::sub(gl::dbl(c0[i]), gl::add(gl::dbl(d0[i]), d0[i]));
-        c1[i] = gl::sub(gl::dbl(c1[i]), gl::add(gl::dbl(d1[i]), d1[i]));
+        c0[i] = q_sub(q_dbl(c0[i]), q_add(q_dbl(d0[i]), d0[i]));
+        c1[i] = q_sub(q_dbl(c1[i]), q_add(q_dbl(d1[i]), d1[i]));
       }
     }
     mz(E, S, i0, c0, A + 228);
     mz(E, S, i0, c1, A + 308);
 #pragma unroll 2
-    for (int i = 0; i < 32; i++) E.term(gl::sub(TL(i0, a + 32 + i), TL(i0, b + 32 + i)));
+    for (int i = 0; i < 32; i++) E.term(q_sub(TL(i0, a + 32 + i), TL(i0, b + 32 + i)));
     E.end_group(is_x_eq_filter);
     // x
     ext_conv(S, l0, l1, l0, l1, c0, c1);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      c0[i] = gl::sub(c0[i], gl::add(gl::add(TL(i0, a + i), TL(i0, b + i)), TL(i0, c + i)));
-      c1[i] = gl::sub(c1[i], gl::add(gl::add(TL(i0, a + 16 + i), TL(i0, b + 16 + i)), TL(i0, c + 16 + i)));
+      c0[i] = q_sub(c0[i], q_add(q_add(TL(i0, a + i), TL(i0, b + i)), TL(i0, c + i)));
+      c1[i] = q_sub(c1[i], q_add(q_add(TL(i0, a + 16 + i), TL(i0, b + 16 + i)), TL(i0, c + 16 + i)));
     }
     mz(E, S, i0, c0, A + 388);
     mz(E, S, i0, c1, A + 468);
     // y
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      u0[i] = gl::sub(TL(i0, c + i), TL(i0, a + i));
-      u1[i] = gl::sub(TL(i0, c + 16 + i), TL(i0, a + 16 + i));
+      u0[i] = q_sub(TL(i0, c + i), TL(i0, a + i));
+      u1[i] = q_sub(TL(i0, c + 16 + i), TL(i0, a + 16 + i));
     }
     ext_conv(S, l0, l1, u0, u1, c0, c1);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      c0[i] = gl::add(c0[i], gl::add(TL(i0, c + 32 + i), TL(i0, a + 32 + i)));
-      c1[i] = gl::add(c1[i], gl::add(TL(i0, c + 48 + i), TL(i0, a + 48 + i)));
+      c0[i] = q_add(c0[i], q_add(TL(i0, c + 32 + i), TL(i0, a + 32 + i)));
+      c1[i] = q_add(c1[i], q_add(TL(i0, c + 48 + i), TL(i0, a + 48 + i)));
     }
     mz(E, S, i0, c0, A + 548);
     mz(E, S, i0, c1, A + 628);
@@ -298,7 +325,7 @@ struct QuotientK {
     ld16(i0, Y::b, y);
     conv31(x, y, in);
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) in[i] = gl::sub(in[i], TL(i0, Y::c + i));
+    for (int i = 0; i < 16; i++) in[i] = q_sub(in[i], TL(i0, Y::c + i));
     mz(E, S, i0, in, Y::aux);
     E.end_group(filter);
   }
@@ -306,7 +333,7 @@ struct QuotientK {
   // n terms  X[i] - Y[i]  where X, Y are columns of the local (sel 0) or next (sel 1) row
   PB_HD void eq_terms(Emit& E, size_t ix, int colx, size_t iy, int coly, int n) const {
 #pragma unroll 2
-    for (int i = 0; i < n; i++) E.term(gl::sub(TL(ix, colx + i), TL(iy, coly + i)));
+    for (int i = 0; i < n; i++) E.term(q_sub(TL(ix, colx + i), TL(iy, coly + i)));
   }
 
   PB_HD void operator()(size_t i) const {
@@ -332,17 +359,17 @@ struct QuotientK {
     else
       mul_fq(E, S, i0, filter);
     // first round
-    E.term(gl::sub(TL(i0, Y::flag_op), 1));
+    E.term(q_sub(TL(i0, Y::flag_op), 1));
     eq_terms(E, i0, Y::reg0, i0, Y::b, L);
     E.end_group(is_first);
     const u64 bit0 = TL(i0, Y::bits);
     eq_terms(E, i0, Y::reg1, i0, Y::c, L);
-    E.end_group(gl::mul(bit0, is_first));
+    E.end_group(q_mul(bit0, is_first));
     eq_terms(E, i0, Y::reg1, i0, Y::a, L);
-    E.end_group(gl::mul(gl::sub(1, bit0), is_first));
+    E.end_group(q_mul(q_sub(1, bit0), is_first));
     if (KIND == 2) {
 #pragma unroll 1
-      for (int k = 0; k < 16; k++) E.term(gl::sub(TL(i0, Y::a + k), k == 0 ? 1 : 0));
+      for (int k = 0; k < 16; k++) E.term(q_sub(TL(i0, Y::a + k), k == 0 ? 1 : 0));
       E.end_group(is_first);
     }
     // doubling / squaring step -> adding / multiplying step
@@ -351,52 +378,52 @@ struct QuotientK {
     eq_terms(E, i1, Y::b, i0, Y::reg0, L);
     E.end_group(fs);
     eq_terms(E, i1, Y::reg1, i1, Y::c, L);
-    E.end_group(gl::mul(nbit0, fs));
+    E.end_group(q_mul(nbit0, fs));
     eq_terms(E, i1, Y::reg1, i1, Y::a, L);
-    E.end_group(gl::mul(gl::sub(1, nbit0), fs));
+    E.end_group(q_mul(q_sub(1, nbit0), fs));
     eq_terms(E, i1, Y::reg0, i0, Y::reg0, L);
-    E.term(gl::sub(TL(i1, Y::flag_op), 1));
+    E.term(q_sub(TL(i1, Y::flag_op), 1));
     E.term(TL(i1, Y::flag_sq));
 #pragma unroll 2
-    for (int k = 0; k < 256; k++) E.term(gl::sub(TL(i1, Y::bits + k), TL(i0, Y::bits + ((k + 1) & 255))));
+    for (int k = 0; k < 256; k++) E.term(q_sub(TL(i1, Y::bits + k), TL(i0, Y::bits + ((k + 1) & 255))));
     E.end_group(fs);
     // adding / multiplying step -> doubling / squaring step
     const u64 g = TL(i0, Y::flag_op);
-    const u64 is_next_not_last = gl::sub(TL(i1, Y::filter), TL(i1, Y::rf + 1));
+    const u64 is_next_not_last = q_sub(TL(i1, Y::filter), TL(i1, Y::rf + 1));
     eq_terms(E, i1, Y::a, i0, Y::reg0, L);
     eq_terms(E, i1, Y::b, i0, Y::reg0, L);
     eq_terms(E, i1, Y::reg1, i0, Y::reg1, L);
     eq_terms(E, i1, Y::reg0, i1, Y::c, L);
     E.term(TL(i1, Y::flag_op));
-    E.term(gl::sub(TL(i1, Y::flag_sq), is_next_not_last));
+    E.term(q_sub(TL(i1, Y::flag_sq), is_next_not_last));
     eq_terms(E, i1, Y::bits, i0, Y::bits, 256);
     E.end_group(g);
     // round flags (8 constraints, written out with their own factors)
     {
       const u64 counter = TL(i0, Y::rf + 2), inv_c = TL(i0, Y::rf + 3), inv_cp = TL(i0, Y::rf + 4);
       const u64 next_counter = TL(i1, Y::rf + 2);
-      const u64 not_filter = gl::sub(1, filter);
-      E.term(gl::mul(not_filter, is_first));
-      E.term(gl::mul(not_filter, is_last));
-      E.term(gl::mul(filter, gl::sub(gl::mul(counter, inv_c), gl::sub(1, is_first))));
-      E.term(gl::mul(gl::mul(filter, counter), is_first));
-      const u64 cprime = gl::sub(counter, (u64)(tg::PERIOD - 1));
-      E.term(gl::mul(filter, gl::sub(gl::mul(cprime, inv_cp), gl::sub(1, is_last))));
-      E.term(gl::mul(gl::mul(filter, cprime), is_last));
-      E.term(gl::mul(gl::mul(filter, gl::sub(1, is_last)), gl::sub(gl::sub(next_counter, counter), 1)));
-      E.term(gl::mul(gl::mul(filter, is_last), next_counter));
+      const u64 not_filter = q_sub(1, filter);
+      E.term(q_mul(not_filter, is_first));
+      E.term(q_mul(not_filter, is_last));
+      E.term(q_mul(filter, q_sub(q_mul(counter, inv_c), q_sub(1, is_first))));
+      E.term(q_mul(q_mul(filter, counter), is_first));
+      const u64 cprime = q_sub(counter, (u64)(tg::PERIOD - 1));
+      E.term(q_mul(filter, q_sub(q_mul(cprime, inv_cp), q_sub(1, is_last))));
+      E.term(q_mul(q_mul(filter, cprime), is_last));
+      E.term(q_mul(q_mul(filter, q_sub(1, is_last)), q_sub(q_sub(next_counter, counter), 1)));
+      E.term(q_mul(q_mul(filter, is_last), next_counter));
       E.end_group(1);
     }
     // timestamp and filter continuity
-    E.term(gl::sub(TL(i1, Y::ts), TL(i0, Y::ts)));
-    E.term(gl::sub(TL(i1, Y::filter), filter));
-    E.end_group(gl::sub(filter, is_last));
+    E.term(q_sub(TL(i1, Y::ts), TL(i0, Y::ts)));
+    E.term(q_sub(TL(i1, Y::filter), filter));
+    E.end_group(q_sub(filter, is_last));
     // range counter
     {
-      const u64 rc = TL(i0, Y::rc), d = gl::sub(TL(i1, Y::rc), rc);
-      E.term(gl::sub(gl::sqr(d), d));
+      const u64 rc = TL(i0, Y::rc), d = q_sub(TL(i1, Y::rc), rc);
+      E.term(q_sub(q_sqr(d), d));
       E.end_group(z_last);
-      E.term(gl::sub(rc, 65535));
+      E.term(q_sub(rc, 65535));
       E.end_group(l_last);
     }
     // logUp lookups (auxiliary columns: per challenge NH helpers then Z)
@@ -404,54 +431,68 @@ struct QuotientK {
     for (int j = 0; j < nch; j++) {
       const u64 beta = p.ch.beta[j];
       const u64* hcol = p.ax + (size_t)(j * (Y::NH + 1)) * p.ax_stride;
-      u64 hs = 0;
+      gl::Acc hsum;
       for (int k = 0; k < Y::NH; k++) {
         const u64 h = hcol[(size_t)k * p.ax_stride + a0];
-        hs = gl::add(hs, h);
-        const u64 c0 = gl::add(TL(i0, Y::rc_lo + 2 * k), beta);
+        hsum.addv(h);
+        const u64 c0 = q_add(TL(i0, Y::rc_lo + 2 * k), beta);
         if (2 * k + 1 < Y::NCOLS) {
-          const u64 c1 = gl::add(TL(i0, Y::rc_lo + 2 * k + 1), beta);
-          E.term(gl::sub(gl::sub(gl::mul(gl::mul(c1, c0), h), c1), c0));
+          const u64 c1 = q_add(TL(i0, Y::rc_lo + 2 * k + 1), beta);
+          E.term(q_sub(q_sub(q_mul(q_mul(c1, c0), h), c1), c0));
         } else {
-          E.term(gl::sub(gl::mul(c0, h), 1));
+          E.term(q_sub(q_mul(c0, h), 1));
         }
       }
       E.end_group(1);
       const u64 z = hcol[(size_t)Y::NH * p.ax_stride + a0], nz = hcol[(size_t)Y::NH * p.ax_stride + a1];
       E.term(z);
       E.end_group(l_first);
-      const u64 table = gl::add(TL(i0, Y::rc), beta);
-      const u64 yv = gl::sub(gl::mul(hs, table), TL(i0, Y::freq));
-      E.term(gl::sub(gl::mul(gl::sub(nz, z), table), yv));
+      const u64 hs = hsum.reduce();
+      const u64 table = q_add(TL(i0, Y::rc), beta);
+      const u64 yv = q_sub(q_mul(hs, table), TL(i0, Y::freq));
+      E.term(q_sub(q_mul(q_sub(nz, z), table), yv));
       E.end_group(1);
     }
-    // cross-table lookups: CTL-major, challenge-minor
+    // cross-table lookups: CTL-major, challenge-minor. comb = sum_k v_k beta^k + gamma as a lazy dot product with
+    // the beta powers (p.bpow[j][k]); the 16 scalar limbs (le_bits sums) are computed once for all challenges.
     {
       const u64* zc = p.ax + (size_t)((Y::NH + 1) * nch) * p.ax_stride;
+      u64 limbs[16];
+#pragma unroll 1
+      for (int k = 0; k < 16; k++) {
+        gl::Acc s16;
+#pragma unroll 4
+        for (int b = 0; b < 16; b++) s16.mac(TL(i0, Y::bits + 16 * k + b), (u64)1 << b);
+        limbs[k] = s16.reduce();
+      }
       for (int c = 0; c < 2; c++) {
         const u64 f = c == 0 ? is_first : is_last;
         // looked columns: c = 0: x (b), offset (a, curves only), s limbs, timestamp;  c = 1: reg1, timestamp
         for (int j = 0; j < nch; j++) {
-          const u64 beta = p.ch.beta[j];
-          u64 comb = TL(i0, Y::ts);
+          const u64* bp = p.bpow + (size_t)j * p.bpow_stride;
+          gl::Acc cs;
+          int e = 0;
           if (c == 0) {
-            for (int k = 15; k >= 0; k--) {
-              u64 limb = 0;
-              for (int b = 15; b >= 0; b--) limb = gl::add(gl::dbl(limb), TL(i0, Y::bits + 16 * k + b));
-              comb = gl::add(gl::mul(comb, beta), limb);
+#pragma unroll 4
+            for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::b + k), bp[e++]);
+            if (KIND != 2) {
+#pragma unroll 4
+              for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::a + k), bp[e++]);
             }
-            if (KIND != 2)
-              for (int k = L - 1; k >= 0; k--) comb = gl::add(gl::mul(comb, beta), TL(i0, Y::a + k));
-            for (int k = L - 1; k >= 0; k--) comb = gl::add(gl::mul(comb, beta), TL(i0, Y::b + k));
+#pragma unroll 4
+            for (int k = 0; k < 16; k++) cs.mac(limbs[k], bp[e++]);
           } else {
-            for (int k = L - 1; k >= 0; k--) comb = gl::add(gl::mul(comb, beta), TL(i0, Y::reg1 + k));
+#pragma unroll 4
+            for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::reg1 + k), bp[e++]);
           }
-          comb = gl::add(comb, p.ch.gamma[j]);
+          cs.mac(TL(i0, Y::ts), bp[e]);
+          cs.addv(p.ch.gamma[j]);
+          const u64 comb = cs.reduce();
           const u64 lz = zc[(size_t)(c * nch + j) * p.ax_stride + a0];
           const u64 nz = zc[(size_t)(c * nch + j) * p.ax_stride + a1];
-          E.term(gl::sub(gl::mul(comb, lz), f));
+          E.term(q_sub(q_mul(comb, lz), f));
           E.end_group(l_last);
-          E.term(gl::sub(gl::mul(comb, gl::sub(lz, nz)), f));
+          E.term(q_sub(q_mul(comb, q_sub(lz, nz)), f));
           E.end_group(z_last);
         }
       }
