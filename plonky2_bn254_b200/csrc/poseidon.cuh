@@ -191,9 +191,9 @@ __device__ __forceinline__ void mds_rc(u64 s[12], const u64* rc2) {
   }
   mds_rows<0>(s, X, rc2);
 }
-// The whole permutation is ONE loop over the 30 rounds with one copy of the S-box code (three lanes at a
-// time, lanes rotated through fixed registers) and one copy of the MDS code: ~1.7 k instructions, so it
-// stays inside the 32 KB L1.5 instruction cache. (Straight-line code per round type was 12.6 k
+// The whole permutation has one copy of the 12-lane S-box code (three lanes at a time, lanes rotated through
+// fixed registers) and two copies of the MDS code: ~1.7 k instructions, so it stays inside the 32 KB L1.5
+// instruction cache. (Straight-line code per round type was 12.6 k
 // instructions and ran at a 51 % instruction-cache hit rate - ncu, profiles/r1_*.)
 __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
 #pragma unroll
@@ -203,9 +203,14 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
     if (t < k) t += gl::EPS;
     s[i] = t;
   }
+  // two passes over { 4 full rounds; in the first pass also the 22 partial rounds }: one copy of the 12-lane
+  // S-box code, and the partial rounds as their own straight-line body, so that the scheduler overlaps the serial
+  // S-box chain of lane 0 with the dp2a products of the other lanes
 #pragma unroll 1
-  for (int r = 0; r < N_ROUNDS; r++) {
-    if (r < HALF_FULL || r >= HALF_FULL + N_PARTIAL) {
+  for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+    for (int r4 = 0; r4 < HALF_FULL; r4++) {
+      const int r = phase * (HALF_FULL + N_PARTIAL) + r4;
 #pragma unroll 1
       for (int j = 0; j < 4; j++) {
         const u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]);
@@ -215,10 +220,15 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
         s[10] = t1;
         s[11] = t2;
       }
-    } else {
-      s[0] = sbox(s[0]);
+      mds_rc(s, rc2 + (r + 1) * 24);
     }
-    mds_rc(s, rc2 + (r + 1) * 24);
+    if (phase == 0) {
+#pragma unroll 1
+      for (int r = HALF_FULL; r < HALF_FULL + N_PARTIAL; r++) {
+        s[0] = sbox(s[0]);
+        mds_rc(s, rc2 + (r + 1) * 24);
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = s[i] >= gl::P ? s[i] - gl::P : s[i];

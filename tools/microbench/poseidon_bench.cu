@@ -162,6 +162,32 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
     if (t < k) t += EPS;
     s[i] = t;
   }
+#ifdef SPLIT_LOOPS
+  // partial rounds as their own straight-line body so that the scheduler can overlap the serial S-box chain of
+  // lane 0 with the dp2a products of the other lanes
+#pragma unroll 1
+  for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+    for (int r4 = 0; r4 < 4; r4++) {
+      const int r = phase * 26 + r4;
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) {
+        const u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]);
+#pragma unroll
+        for (int i = 0; i < 9; i++) s[i] = s[i + 3];
+        s[9] = t0; s[10] = t1; s[11] = t2;
+      }
+      mds_rc(s, rc2 + (r + 1) * 24);
+    }
+    if (phase == 0) {
+#pragma unroll 1
+      for (int r = 4; r < 26; r++) {
+        s[0] = sbox(s[0]);
+        mds_rc(s, rc2 + (r + 1) * 24);
+      }
+    }
+  }
+#else
 #pragma unroll 1
   for (int r = 0; r < 30; r++) {
     if (r < 4 || r >= 26) {
@@ -177,6 +203,7 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
     }
     mds_rc(s, rc2 + (r + 1) * 24);
   }
+#endif
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = s[i] >= P ? s[i] - P : s[i];
 }
