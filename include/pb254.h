@@ -140,6 +140,12 @@ int pb254_verify(const uint64_t* proof_words, size_t n_words, const uint64_t* in
  * 10-word header {magic, kind, degree_bits, config[7]} (layout in DESIGN.md). */
 size_t pb254_proof_words(const pb254_proof* proof);
 const uint64_t* pb254_proof_data(const pb254_proof* proof);
+/* The batch's native outputs, read from the trace instead of being recomputed on the CPU: for instance k the
+ * 16-bit limbs (one per word) of s*x + offset (G1: x, y; G2: x.c0, x.c1, y.c0, y.c1) or x^s (Fq). run_once
+ * computes exactly these with arkworks before proving (src/generators/g1/stark_proof.rs:143-149) and the MSM
+ * helpers chain them (src/utils/g1_msm.rs:22-36). Only filled by pb254_prove / pb254_prove_dev. */
+size_t pb254_proof_results_words(const pb254_proof* proof);
+const uint64_t* pb254_proof_results_data(const pb254_proof* proof);
 /* intermediate artefacts for parity tests (only when keep_debug != 0): which = 0 auxiliary values
  * (A x n), 1 quotient chunk coefficients (2*num_challenges x n), 2 challenges, 3 query indices */
 size_t pb254_proof_debug_words(const pb254_proof* proof, int which);

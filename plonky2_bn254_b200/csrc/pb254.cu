@@ -14,6 +14,7 @@ unsigned long long g_pb_launches = 0;
 
 struct pb254_proof {
   prover::ProofData data;
+  std::vector<u64> results;  // n_inputs x L limbs (pb254_prove / pb254_prove_dev only)
 };
 
 namespace {
@@ -58,6 +59,19 @@ void throw_trace_error(int herr) {
     throw Pb254Error(PB254_E_INFINITY, "an intermediate sum is the point at infinity (a = -b), unsupported by design");
   if (herr) throw Pb254Error(PB254_E_BAD_ARG, "trace generation: witness consistency check failed");
 }
+
+// results[k][i] = limb i of the `sum` / `product` register at the last row of instance k: s * x + offset (x^s)
+struct GatherResultsK {
+  const u64* trace;
+  u64* out;
+  size_t n_rows;
+  int reg1, L;
+  PB_HD void operator()(size_t gid) const {
+    size_t k = gid / L;
+    int i = (int)(gid % L);
+    out[gid] = trace[(size_t)(reg1 + i) * n_rows + k * tg::PERIOD + (tg::PERIOD - 1)];
+  }
+};
 
 struct PermuteK {
   const u64* in;
@@ -257,6 +271,7 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
     c->times.clear();
     u64* d_trace = c->arena.alloc_n<u64>(twords);
     size_t mark = c->arena.off;
+    std::vector<u64> results;
     {
       prover::Stage st(c, "tracegen");
       const u64 *d_in = inputs, *d_ts = timestamps;
@@ -273,11 +288,16 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
       tg::generate(c->arena, kind, d_in, d_ts, n_inputs, n_rows, d_trace, d_err, c->stream);
       int herr = 0;
       pb_d2h(&herr, d_err, sizeof(int), c->stream);
+      u64* d_res = c->arena.alloc_n<u64>(n_inputs * l.L);
+      pb_launch("gather results", GatherResultsK{d_trace, d_res, n_rows, l.reg1, l.L}, n_inputs * l.L, c->stream, 128);
+      results.resize(n_inputs * l.L);
+      pb_d2h(results.data(), d_res, results.size() * 8, c->stream);
       pb_sync(c->stream);
       throw_trace_error(herr);
     }
     c->arena.off = mark;
     pb254_proof* pf = new pb254_proof();
+    pf->results.swap(results);
     try {
       prover::prove_device(c, kind, d_trace, n_rows, cfg, pf->data, keep_debug != 0);
     } catch (...) {
@@ -402,6 +422,8 @@ int pb254_verify(const uint64_t* proof_words, size_t n_words, const uint64_t* in
 }
 
 void pb254_proof_free(pb254_proof* p) { delete p; }
+size_t pb254_proof_results_words(const pb254_proof* p) { return p->results.size(); }
+const uint64_t* pb254_proof_results_data(const pb254_proof* p) { return p->results.data(); }
 size_t pb254_proof_words(const pb254_proof* p) { return p->data.blob.size(); }
 const uint64_t* pb254_proof_data(const pb254_proof* p) { return p->data.blob.data(); }
 // debug artefacts kept when keep_debug != 0: 0 auxiliary values (A x n), 1 quotient chunk coefficients

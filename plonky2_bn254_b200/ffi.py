@@ -77,6 +77,10 @@ class Library:
         L.pb254_proof_debug_data.restype = C.POINTER(C.c_uint64)
         L.pb254_proof_debug_data.argtypes = [C.c_void_p, C.c_int]
         L.pb254_proof_free.argtypes = [C.c_void_p]
+        L.pb254_proof_results_words.restype = C.c_size_t
+        L.pb254_proof_results_words.argtypes = [C.c_void_p]
+        L.pb254_proof_results_data.restype = C.POINTER(C.c_uint64)
+        L.pb254_proof_results_data.argtypes = [C.c_void_p]
 
     def check(self, rc):
         if rc != 0:
@@ -266,6 +270,14 @@ class Proof:
 
     def bytes(self) -> bytes:
         return self.words().tobytes()
+
+    def results(self) -> np.ndarray:
+        """(n_inputs, L) 16-bit limbs of the native outputs s*x + offset / x^s, read from the trace."""
+        n = self.L.lib.pb254_proof_results_words(self._h)
+        if n == 0:
+            return np.zeros((0, 0), dtype=np.uint64)
+        p = self.L.lib.pb254_proof_results_data(self._h)
+        return np.ctypeslib.as_array(p, shape=(n,)).copy()
 
     def debug(self, which: int) -> np.ndarray:
         n = self.L.lib.pb254_proof_debug_words(self._h, which)

@@ -101,3 +101,12 @@ def test_product_verifier_accepts_gpu_proofs(gpu_ctx, kind, k):
     with pytest.raises(ffi.Pb254Error) as e:
         gpu_ctx.L.verify(w, inp, ts)
     assert e.value.code == 7
+
+
+@pytest.mark.parametrize("kind,k", [(I.KIND_G1, 5), (I.KIND_G2, 2), (I.KIND_FQ, 4)])
+def test_results_are_the_native_outputs(gpu_ctx, oracle, kind, k):
+    """pb254_proof_results: s*x + offset / x^s per instance, as run_once computes natively (stark_proof.rs:143-149)."""
+    inp, ts = I.make_inputs(kind, k, I.config_seed(90 + kind))
+    res = gpu_ctx.prove(kind, inp, ts).results().reshape(k, -1)
+    for i in range(k):
+        assert (res[i] == oracle.native_result(kind, inp[i])).all()

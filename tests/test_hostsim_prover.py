@@ -20,6 +20,10 @@ def test_hostsim_proof_is_byte_identical(hostsim_ctx, oracle, fq_case):
     assert (pf.debug(0) == ref.debug(0)).all()  # auxiliary columns
     assert (pf.debug(1) == ref.debug(1)).all()  # quotient chunks
     assert w.size == fq_case["words"].size and (w == fq_case["words"]).all()
+    # the native outputs x^s, read from the trace (pb254_proof_results)
+    res = pf.results().reshape(3, -1)
+    for i in range(3):
+        assert (res[i] == oracle.native_result(fq_case["kind"], fq_case["inputs"][i])).all()
     # prove_trace (the literal prove() signature on a host trace) gives the same bytes
     pf2 = hostsim_ctx.prove_trace(fq_case["kind"], fq_case["trace"])
     assert (pf2.words() == w).all()
@@ -35,3 +39,4 @@ def test_hostsim_commit_matches_oracle(hostsim_ctx, oracle):
     coeffs, lde = oracle.lde_batch(v, 1)
     assert (hostsim_ctx.lde_batch(v, 1) == lde).all()
     assert (hostsim_ctx.lde_batch(coeffs, 1, from_coeffs=True) == lde).all()
+
