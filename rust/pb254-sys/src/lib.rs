@@ -67,6 +67,14 @@ extern "C" {
     pub fn pb254_proof_free(proof: *mut pb254_proof);
     pub fn pb254_verify(proof_words: *const u64, n_words: usize, inputs: *const u64, timestamps: *const u64,
                         n_inputs: usize) -> c_int;
+    pub fn pb254_proof_results_words(proof: *const pb254_proof) -> usize;
+    pub fn pb254_proof_results_data(proof: *const pb254_proof) -> *const u64;
+    pub fn pb254_lde_dev(ctx: *mut pb254_ctx, d_values: *const u64, cols: usize, n: usize, rate_bits: u32,
+                         from_coeffs: c_int, d_lde_out: *mut u64) -> c_int;
+    pub fn pb254_leaf_hash_rows_dev(ctx: *mut pb254_ctx, d_matrix: *const u64, stride: usize, cols: usize, rows: usize,
+                                    d_digests_out: *mut u64) -> c_int;
+    pub fn pb254_merkle_subtree_dev(ctx: *mut pb254_ctx, d_all_digests: *const u64, log_total: u32, first: usize,
+                                    log_sub: u32, log_roots: u32, d_roots_out: *mut u64) -> c_int;
     pub fn pb254_proof_words(proof: *const pb254_proof) -> usize;
     pub fn pb254_proof_data(proof: *const pb254_proof) -> *const u64;
     pub fn pb254_proof_debug_words(proof: *const pb254_proof, which: c_int) -> usize;
