@@ -170,7 +170,11 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
 #pragma unroll 1
     for (int r4 = 0; r4 < 4; r4++) {
       const int r = phase * 26 + r4;
+#ifdef UNROLL_SBOX
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
       for (int j = 0; j < 4; j++) {
         const u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]);
 #pragma unroll
