@@ -180,7 +180,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -358,12 +358,36 @@ def run_ours(args, rank, world, local_rank):
     }
     if not args.no_cpu_baseline and world >= 1:
         line["cpu_baseline"] = cpu_baseline(args.instances, args.cpu_sample_instances)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL prints its version banner, torchrun its OMP note)
+    write to fd 1 on their own, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a saved
+    copy of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
