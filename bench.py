@@ -326,10 +326,11 @@ def run_ours(args, rank, world, local_rank):
         "poseidon_permutations_per_launch": lead_perms,
         "poseidon_gperm_per_s": lead_perms / (lead_ms * 1e-3) / 1e9 if lead_ms > 0 else 0.0,
         "int_pipe": {
-            "thread_instructions_per_permutation": 25.6e3,
-            "issue_peak_gperm_per_s": 148 * 128 * 1.965e9 / 25.6e3 / 1e9,
-            "note": "ncu (profiles/r1_leafhash_final.txt): issue-active 70 %, ALU pipe 56 %, FMA pipe 39 % of "
-                    "peak; the kernel is bound by instruction issue on the integer pipes, not by HBM"},
+            "thread_instructions_per_permutation": 25.0e3,
+            "issue_peak_gperm_per_s": 148 * 128 * 1.965e9 / 25.0e3 / 1e9,
+            "fma_heavy_pipe_busy": 0.85, "alu_pipe_busy": 0.64, "issue_active": 0.71,
+            "note": "ncu (profiles/r1_kernels_final.md): the FMA-heavy pipe (IMAD / IDP) is 85 % busy, issue slots "
+                    "71 %; the kernel is bound by the integer pipes, not by HBM"},
         "all_trees": {"algorithmic_bytes_per_proof": merkle_bytes, "ms_per_proof": merkle_ms,
                       "achieved_gb_s": merkle_bytes / (merkle_ms * 1e-3) / 1e9 if merkle_ms > 0 else 0.0,
                       "poseidon_permutations_per_proof": leaf_perms},
