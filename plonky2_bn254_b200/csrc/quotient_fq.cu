@@ -3,6 +3,10 @@
 
 namespace quot {
 
-void run_fq(const Params& p, pbStream s) { pb_launch("quotient fq", QuotientK<2>{p}, p.size, s, 64); }
+void run_fq(const Params& p, pbStream s) {
+  pb_launch("quotient fq pass 0", QuotientK<2, 0>{p}, p.size, s, 64);
+  pb_launch("quotient fq pass 2", QuotientK<2, 2>{p}, p.size, s, 64);
+  pb_launch("quotient fq pass 3", QuotientK<2, 3>{p}, p.size, s, 64);
+}
 
 }  // namespace quot

@@ -153,10 +153,24 @@ struct Scratch {
   u64 c0[31], c1[31], d0[31], d1[31], t[31], v[33];
 };
 
-template <int KIND>
+// The constraint system is evaluated in NPASS kernels over the same points (PASS = 0 .. NPASS-1), each adding its
+// share of sum_k w_k c_k to the output; the last one divides by Z_H. One kernel for everything needed 104
+// registers and a 2.4 KB scratch frame per thread and ran latency-bound at 24 % warps active (ncu,
+// profiles/r1_kernels_final.md); the passes are smaller programs with higher occupancy.
+//   PASS 0  addition / multiplication gadget, first part (is-zero test, slope)
+//   PASS 1  addition gadget, second part (x and y modulus-zero checks); empty for fq_exp
+//   PASS 2  register equalities, bit rotations, round flags, timestamp, range counter
+//   PASS 3  logUp lookups, cross-table lookups, division by Z_H
+static constexpr int NPASS = 4;
+
+template <int KIND, int PASS>
 struct QuotientK {
   Params p;
   typedef LY<KIND> Y;
+  // constraints emitted before each pass (SURVEY.md Appendix D order)
+  static constexpr int N_ADD1 = KIND == 0 ? 132 : KIND == 1 ? 264 : 33;
+  static constexpr int N_ADD = KIND == 0 ? 198 : KIND == 1 ? 396 : 33;
+  static constexpr int K0 = PASS == 0 ? 0 : PASS == 1 ? N_ADD1 : PASS == 2 ? N_ADD : Y::BASE_CONSTRAINTS;
 
   PB_HD u64 TL(size_t i0, int c) const { return p.tr[(size_t)c * p.tr_stride + i0]; }
 
@@ -190,12 +204,17 @@ struct QuotientK {
 
   PB_HD void add_g1(Emit& E, Scratch& S, size_t i0, u64 filter) const {
     const int A = Y::aux, a = Y::a, b = Y::b, c = Y::c;
+    u64 *lam = S.l0, *t0 = S.u0, *in = S.c0, *in2 = S.d0;
+    if (PASS == 1) {
+      ld16(i0, A + 98, lam);
+      add_g1_xy(E, S, i0, filter);
+      return;
+    }
     imz(E, S, i0, b, a, A, A + 1);
     E.end_group(filter);
     u64 is_x_eq = TL(i0, A), is_x_eq_filter = TL(i0, A + 97);
     E.term(q_sub(q_mul(filter, is_x_eq), is_x_eq_filter));
     E.end_group(1);
-    u64 *lam = S.l0, *t0 = S.u0, *in = S.c0, *in2 = S.d0;
     ld16(i0, A + 98, lam);
     // a.x != b.x : lambda * dx - (b.y - a.y)
 #pragma unroll 1
@@ -216,6 +235,10 @@ struct QuotientK {
 #pragma unroll 1
     for (int i = 0; i < 16; i++) E.term(q_sub(TL(i0, a + 16 + i), TL(i0, b + 16 + i)));
     E.end_group(is_x_eq_filter);
+  }
+  PB_HD void add_g1_xy(Emit& E, Scratch& S, size_t i0, u64 filter) const {
+    const int A = Y::aux, a = Y::a, b = Y::b, c = Y::c;
+    u64 *lam = S.l0, *t0 = S.u0, *in = S.c0;
     // x : lambda^2 - (a.x + b.x + c.x)
     conv31(lam, lam, in);
 #pragma unroll 1
@@ -247,7 +270,13 @@ struct QuotientK {
   }
 
   PB_HD void add_g2(Emit& E, Scratch& S, size_t i0, u64 filter) const {
-    const int A = Y::aux, a = Y::a, b = Y::b, c = Y::c;  // points: x.c0 | x.c1 | y.c0 | y.c1
+    const int A = Y::aux, a = Y::a, b = Y::b;  // points: x.c0 | x.c1 | y.c0 | y.c1
+    if (PASS == 1) {
+      ld16(i0, A + 196, S.l0);
+      ld16(i0, A + 212, S.l1);
+      add_g2_xy(E, S, i0, filter);
+      return;
+    }
     u64 is_x_eq = TL(i0, A), z0 = TL(i0, A + 1), z1 = TL(i0, A + 2);
     E.term(q_sub(q_mul(z0, z1), is_x_eq));
     imz(E, S, i0, b, a, A + 1, A + 3);
@@ -293,6 +322,10 @@ struct QuotientK {
 #pragma unroll 2
     for (int i = 0; i < 32; i++) E.term(q_sub(TL(i0, a + 32 + i), TL(i0, b + 32 + i)));
     E.end_group(is_x_eq_filter);
+  }
+  PB_HD void add_g2_xy(Emit& E, Scratch& S, size_t i0, u64 filter) const {
+    const int A = Y::aux, a = Y::a, b = Y::b, c = Y::c;
+    u64 *l0 = S.l0, *l1 = S.l1, *u0 = S.u0, *u1 = S.u1, *c0 = S.c0, *c1 = S.c1;
     // x
     ext_conv(S, l0, l1, l0, l1, c0, c1);
 #pragma unroll 1
@@ -341,167 +374,181 @@ struct QuotientK {
     const size_t i0 = i * p.step, i1 = i_next * p.step;
     const int nch = p.ch.nch;
     const int L = Y::L;
-    const u64 x = gl::mul(gl::COSET_SHIFT, ntt::tpow(p.t.fwd_lo, p.t.fwd_hi, (u64)i << (ntt::LOG_M - p.log_size)));
-    const u64 z_last = gl::sub(x, p.g_inv);
-    const u64 z_h = p.zh[i & 1];
-    const u64 l_first = gl::mul(z_h, gl::inv(gl::mul(p.n_field, gl::sub(x, 1))));
-    const u64 l_last = gl::mul(z_h, gl::inv(gl::mul(p.n_field, gl::sub(gl::mul(p.g, x), 1))));
-
     Emit E(p.weights, nch);
-    if (p.dbg && i == p.dbg_point) E.dbg = p.dbg;
+    E.k = K0;
+    if (p.dbg && i == p.dbg_point) E.dbg = p.dbg + 64 * PASS;
     const u64 filter = TL(i0, Y::filter);
-    const u64 is_first = TL(i0, Y::rf), is_last = TL(i0, Y::rf + 1);
-    Scratch S;
-    if (KIND == 0)
-      add_g1(E, S, i0, filter);
-    else if (KIND == 1)
-      add_g2(E, S, i0, filter);
-    else
-      mul_fq(E, S, i0, filter);
-    // first round
-    E.term(q_sub(TL(i0, Y::flag_op), 1));
-    eq_terms(E, i0, Y::reg0, i0, Y::b, L);
-    E.end_group(is_first);
-    const u64 bit0 = TL(i0, Y::bits);
-    eq_terms(E, i0, Y::reg1, i0, Y::c, L);
-    E.end_group(q_mul(bit0, is_first));
-    eq_terms(E, i0, Y::reg1, i0, Y::a, L);
-    E.end_group(q_mul(q_sub(1, bit0), is_first));
-    if (KIND == 2) {
+    if (PASS <= 1) {
+      Scratch S;
+      if (KIND == 0)
+        add_g1(E, S, i0, filter);
+      else if (KIND == 1)
+        add_g2(E, S, i0, filter);
+      else if (PASS == 0)
+        mul_fq(E, S, i0, filter);
+      if (E.k != (PASS == 0 ? N_ADD1 : N_ADD)) *p.err = 1;
+    } else {
+      const u64 is_first = TL(i0, Y::rf), is_last = TL(i0, Y::rf + 1);
+      const u64 x = gl::mul(gl::COSET_SHIFT, ntt::tpow(p.t.fwd_lo, p.t.fwd_hi, (u64)i << (ntt::LOG_M - p.log_size)));
+      const u64 z_last = gl::sub(x, p.g_inv);
+      const u64 z_h = p.zh[i & 1];
+      const u64 l_last = gl::mul(z_h, gl::inv(gl::mul(p.n_field, gl::sub(gl::mul(p.g, x), 1))));
+      if (PASS == 2) {
+        // first round
+        E.term(q_sub(TL(i0, Y::flag_op), 1));
+        eq_terms(E, i0, Y::reg0, i0, Y::b, L);
+        E.end_group(is_first);
+        const u64 bit0 = TL(i0, Y::bits);
+        eq_terms(E, i0, Y::reg1, i0, Y::c, L);
+        E.end_group(q_mul(bit0, is_first));
+        eq_terms(E, i0, Y::reg1, i0, Y::a, L);
+        E.end_group(q_mul(q_sub(1, bit0), is_first));
+        if (KIND == 2) {
 #pragma unroll 1
-      for (int k = 0; k < 16; k++) E.term(q_sub(TL(i0, Y::a + k), k == 0 ? 1 : 0));
-      E.end_group(is_first);
-    }
-    // doubling / squaring step -> adding / multiplying step
-    const u64 fs = TL(i0, Y::flag_sq), nbit0 = TL(i1, Y::bits);
-    eq_terms(E, i1, Y::a, i0, Y::reg1, L);
-    eq_terms(E, i1, Y::b, i0, Y::reg0, L);
-    E.end_group(fs);
-    eq_terms(E, i1, Y::reg1, i1, Y::c, L);
-    E.end_group(q_mul(nbit0, fs));
-    eq_terms(E, i1, Y::reg1, i1, Y::a, L);
-    E.end_group(q_mul(q_sub(1, nbit0), fs));
-    eq_terms(E, i1, Y::reg0, i0, Y::reg0, L);
-    E.term(q_sub(TL(i1, Y::flag_op), 1));
-    E.term(TL(i1, Y::flag_sq));
+          for (int k = 0; k < 16; k++) E.term(q_sub(TL(i0, Y::a + k), k == 0 ? 1 : 0));
+          E.end_group(is_first);
+        }
+        // doubling / squaring step -> adding / multiplying step
+        const u64 fs = TL(i0, Y::flag_sq), nbit0 = TL(i1, Y::bits);
+        eq_terms(E, i1, Y::a, i0, Y::reg1, L);
+        eq_terms(E, i1, Y::b, i0, Y::reg0, L);
+        E.end_group(fs);
+        eq_terms(E, i1, Y::reg1, i1, Y::c, L);
+        E.end_group(q_mul(nbit0, fs));
+        eq_terms(E, i1, Y::reg1, i1, Y::a, L);
+        E.end_group(q_mul(q_sub(1, nbit0), fs));
+        eq_terms(E, i1, Y::reg0, i0, Y::reg0, L);
+        E.term(q_sub(TL(i1, Y::flag_op), 1));
+        E.term(TL(i1, Y::flag_sq));
 #pragma unroll 2
-    for (int k = 0; k < 256; k++) E.term(q_sub(TL(i1, Y::bits + k), TL(i0, Y::bits + ((k + 1) & 255))));
-    E.end_group(fs);
-    // adding / multiplying step -> doubling / squaring step
-    const u64 g = TL(i0, Y::flag_op);
-    const u64 is_next_not_last = q_sub(TL(i1, Y::filter), TL(i1, Y::rf + 1));
-    eq_terms(E, i1, Y::a, i0, Y::reg0, L);
-    eq_terms(E, i1, Y::b, i0, Y::reg0, L);
-    eq_terms(E, i1, Y::reg1, i0, Y::reg1, L);
-    eq_terms(E, i1, Y::reg0, i1, Y::c, L);
-    E.term(TL(i1, Y::flag_op));
-    E.term(q_sub(TL(i1, Y::flag_sq), is_next_not_last));
-    eq_terms(E, i1, Y::bits, i0, Y::bits, 256);
-    E.end_group(g);
-    // round flags (8 constraints, written out with their own factors)
-    {
-      const u64 counter = TL(i0, Y::rf + 2), inv_c = TL(i0, Y::rf + 3), inv_cp = TL(i0, Y::rf + 4);
-      const u64 next_counter = TL(i1, Y::rf + 2);
-      const u64 not_filter = q_sub(1, filter);
-      E.term(q_mul(not_filter, is_first));
-      E.term(q_mul(not_filter, is_last));
-      E.term(q_mul(filter, q_sub(q_mul(counter, inv_c), q_sub(1, is_first))));
-      E.term(q_mul(q_mul(filter, counter), is_first));
-      const u64 cprime = q_sub(counter, (u64)(tg::PERIOD - 1));
-      E.term(q_mul(filter, q_sub(q_mul(cprime, inv_cp), q_sub(1, is_last))));
-      E.term(q_mul(q_mul(filter, cprime), is_last));
-      E.term(q_mul(q_mul(filter, q_sub(1, is_last)), q_sub(q_sub(next_counter, counter), 1)));
-      E.term(q_mul(q_mul(filter, is_last), next_counter));
-      E.end_group(1);
-    }
-    // timestamp and filter continuity
-    E.term(q_sub(TL(i1, Y::ts), TL(i0, Y::ts)));
-    E.term(q_sub(TL(i1, Y::filter), filter));
-    E.end_group(q_sub(filter, is_last));
-    // range counter
-    {
-      const u64 rc = TL(i0, Y::rc), d = q_sub(TL(i1, Y::rc), rc);
-      E.term(q_sub(q_sqr(d), d));
-      E.end_group(z_last);
-      E.term(q_sub(rc, 65535));
-      E.end_group(l_last);
-    }
-    // logUp lookups (auxiliary columns: per challenge NH helpers then Z)
-    const size_t a0 = i0, a1 = i1;
-    for (int j = 0; j < nch; j++) {
-      const u64 beta = p.ch.beta[j];
-      const u64* hcol = p.ax + (size_t)(j * (Y::NH + 1)) * p.ax_stride;
-      gl::Acc hsum;
-      for (int k = 0; k < Y::NH; k++) {
-        const u64 h = hcol[(size_t)k * p.ax_stride + a0];
-        hsum.addv(h);
-        const u64 c0 = q_add(TL(i0, Y::rc_lo + 2 * k), beta);
-        if (2 * k + 1 < Y::NCOLS) {
-          const u64 c1 = q_add(TL(i0, Y::rc_lo + 2 * k + 1), beta);
-          E.term(q_sub(q_sub(q_mul(q_mul(c1, c0), h), c1), c0));
-        } else {
-          E.term(q_sub(q_mul(c0, h), 1));
+        for (int k = 0; k < 256; k++) E.term(q_sub(TL(i1, Y::bits + k), TL(i0, Y::bits + ((k + 1) & 255))));
+        E.end_group(fs);
+        // adding / multiplying step -> doubling / squaring step
+        const u64 g = TL(i0, Y::flag_op);
+        const u64 is_next_not_last = q_sub(TL(i1, Y::filter), TL(i1, Y::rf + 1));
+        eq_terms(E, i1, Y::a, i0, Y::reg0, L);
+        eq_terms(E, i1, Y::b, i0, Y::reg0, L);
+        eq_terms(E, i1, Y::reg1, i0, Y::reg1, L);
+        eq_terms(E, i1, Y::reg0, i1, Y::c, L);
+        E.term(TL(i1, Y::flag_op));
+        E.term(q_sub(TL(i1, Y::flag_sq), is_next_not_last));
+        eq_terms(E, i1, Y::bits, i0, Y::bits, 256);
+        E.end_group(g);
+        // round flags (8 constraints, written out with their own factors)
+        {
+          const u64 counter = TL(i0, Y::rf + 2), inv_c = TL(i0, Y::rf + 3), inv_cp = TL(i0, Y::rf + 4);
+          const u64 next_counter = TL(i1, Y::rf + 2);
+          const u64 not_filter = q_sub(1, filter);
+          E.term(q_mul(not_filter, is_first));
+          E.term(q_mul(not_filter, is_last));
+          E.term(q_mul(filter, q_sub(q_mul(counter, inv_c), q_sub(1, is_first))));
+          E.term(q_mul(q_mul(filter, counter), is_first));
+          const u64 cprime = q_sub(counter, (u64)(tg::PERIOD - 1));
+          E.term(q_mul(filter, q_sub(q_mul(cprime, inv_cp), q_sub(1, is_last))));
+          E.term(q_mul(q_mul(filter, cprime), is_last));
+          E.term(q_mul(q_mul(filter, q_sub(1, is_last)), q_sub(q_sub(next_counter, counter), 1)));
+          E.term(q_mul(q_mul(filter, is_last), next_counter));
+          E.end_group(1);
         }
-      }
-      E.end_group(1);
-      const u64 z = hcol[(size_t)Y::NH * p.ax_stride + a0], nz = hcol[(size_t)Y::NH * p.ax_stride + a1];
-      E.term(z);
-      E.end_group(l_first);
-      const u64 hs = hsum.reduce();
-      const u64 table = q_add(TL(i0, Y::rc), beta);
-      const u64 yv = q_sub(q_mul(hs, table), TL(i0, Y::freq));
-      E.term(q_sub(q_mul(q_sub(nz, z), table), yv));
-      E.end_group(1);
-    }
-    // cross-table lookups: CTL-major, challenge-minor. comb = sum_k v_k beta^k + gamma as a lazy dot product with
-    // the beta powers (p.bpow[j][k]); the 16 scalar limbs (le_bits sums) are computed once for all challenges.
-    {
-      const u64* zc = p.ax + (size_t)((Y::NH + 1) * nch) * p.ax_stride;
-      u64 limbs[16];
-#pragma unroll 1
-      for (int k = 0; k < 16; k++) {
-        gl::Acc s16;
-#pragma unroll 4
-        for (int b = 0; b < 16; b++) s16.mac(TL(i0, Y::bits + 16 * k + b), (u64)1 << b);
-        limbs[k] = s16.reduce();
-      }
-      for (int c = 0; c < 2; c++) {
-        const u64 f = c == 0 ? is_first : is_last;
-        // looked columns: c = 0: x (b), offset (a, curves only), s limbs, timestamp;  c = 1: reg1, timestamp
-        for (int j = 0; j < nch; j++) {
-          const u64* bp = p.bpow + (size_t)j * p.bpow_stride;
-          gl::Acc cs;
-          int e = 0;
-          if (c == 0) {
-#pragma unroll 4
-            for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::b + k), bp[e++]);
-            if (KIND != 2) {
-#pragma unroll 4
-              for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::a + k), bp[e++]);
-            }
-#pragma unroll 4
-            for (int k = 0; k < 16; k++) cs.mac(limbs[k], bp[e++]);
-          } else {
-#pragma unroll 4
-            for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::reg1 + k), bp[e++]);
-          }
-          cs.mac(TL(i0, Y::ts), bp[e]);
-          cs.addv(p.ch.gamma[j]);
-          const u64 comb = cs.reduce();
-          const u64 lz = zc[(size_t)(c * nch + j) * p.ax_stride + a0];
-          const u64 nz = zc[(size_t)(c * nch + j) * p.ax_stride + a1];
-          E.term(q_sub(q_mul(comb, lz), f));
-          E.end_group(l_last);
-          E.term(q_sub(q_mul(comb, q_sub(lz, nz)), f));
+        // timestamp and filter continuity
+        E.term(q_sub(TL(i1, Y::ts), TL(i0, Y::ts)));
+        E.term(q_sub(TL(i1, Y::filter), filter));
+        E.end_group(q_sub(filter, is_last));
+        // range counter
+        {
+          const u64 rc = TL(i0, Y::rc), d = q_sub(TL(i1, Y::rc), rc);
+          E.term(q_sub(q_sqr(d), d));
           E.end_group(z_last);
+          E.term(q_sub(rc, 65535));
+          E.end_group(l_last);
         }
+        if (E.k != Y::BASE_CONSTRAINTS) *p.err = 1;
+      } else {
+        const u64 l_first = gl::mul(z_h, gl::inv(gl::mul(p.n_field, gl::sub(x, 1))));
+        // logUp lookups (auxiliary columns: per challenge NH helpers then Z)
+        const size_t a0 = i0, a1 = i1;
+        for (int j = 0; j < nch; j++) {
+          const u64 beta = p.ch.beta[j];
+          const u64* hcol = p.ax + (size_t)(j * (Y::NH + 1)) * p.ax_stride;
+          gl::Acc hsum;
+          for (int k = 0; k < Y::NH; k++) {
+            const u64 h = hcol[(size_t)k * p.ax_stride + a0];
+            hsum.addv(h);
+            const u64 c0 = q_add(TL(i0, Y::rc_lo + 2 * k), beta);
+            if (2 * k + 1 < Y::NCOLS) {
+              const u64 c1 = q_add(TL(i0, Y::rc_lo + 2 * k + 1), beta);
+              E.term(q_sub(q_sub(q_mul(q_mul(c1, c0), h), c1), c0));
+            } else {
+              E.term(q_sub(q_mul(c0, h), 1));
+            }
+          }
+          E.end_group(1);
+          const u64 z = hcol[(size_t)Y::NH * p.ax_stride + a0], nz = hcol[(size_t)Y::NH * p.ax_stride + a1];
+          E.term(z);
+          E.end_group(l_first);
+          const u64 hs = hsum.reduce();
+          const u64 table = q_add(TL(i0, Y::rc), beta);
+          const u64 yv = q_sub(q_mul(hs, table), TL(i0, Y::freq));
+          E.term(q_sub(q_mul(q_sub(nz, z), table), yv));
+          E.end_group(1);
+        }
+        // cross-table lookups: CTL-major, challenge-minor. comb = sum_k v_k beta^k + gamma as a lazy dot product with
+        // the beta powers (p.bpow[j][k]); the 16 scalar limbs (le_bits sums) are computed once for all challenges.
+        {
+          const u64* zc = p.ax + (size_t)((Y::NH + 1) * nch) * p.ax_stride;
+          u64 limbs[16];
+#pragma unroll 1
+          for (int k = 0; k < 16; k++) {
+            gl::Acc s16;
+#pragma unroll 4
+            for (int b = 0; b < 16; b++) s16.mac(TL(i0, Y::bits + 16 * k + b), (u64)1 << b);
+            limbs[k] = s16.reduce();
+          }
+          for (int c = 0; c < 2; c++) {
+            const u64 f = c == 0 ? is_first : is_last;
+            // looked columns: c = 0: x (b), offset (a, curves only), s limbs, timestamp;  c = 1: reg1, timestamp
+            for (int j = 0; j < nch; j++) {
+              const u64* bp = p.bpow + (size_t)j * p.bpow_stride;
+              gl::Acc cs;
+              int e = 0;
+              if (c == 0) {
+#pragma unroll 4
+                for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::b + k), bp[e++]);
+                if (KIND != 2) {
+#pragma unroll 4
+                  for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::a + k), bp[e++]);
+                }
+#pragma unroll 4
+                for (int k = 0; k < 16; k++) cs.mac(limbs[k], bp[e++]);
+              } else {
+#pragma unroll 4
+                for (int k = 0; k < L; k++) cs.mac(TL(i0, Y::reg1 + k), bp[e++]);
+              }
+              cs.mac(TL(i0, Y::ts), bp[e]);
+              cs.addv(p.ch.gamma[j]);
+              const u64 comb = cs.reduce();
+              const u64 lz = zc[(size_t)(c * nch + j) * p.ax_stride + a0];
+              const u64 nz = zc[(size_t)(c * nch + j) * p.ax_stride + a1];
+              E.term(q_sub(q_mul(comb, lz), f));
+              E.end_group(l_last);
+              E.term(q_sub(q_mul(comb, q_sub(lz, nz)), f));
+              E.end_group(z_last);
+            }
+          }
+        }
+        if (E.k != Y::BASE_CONSTRAINTS + (Y::NH + 2) * nch + 4 * nch) *p.err = 1;
       }
     }
-    if (E.k != Y::BASE_CONSTRAINTS + (Y::NH + 2) * nch + 4 * nch) *p.err = 1;
-    const u64 zhi = p.zh_inv[i & 1];
+    // accumulate this pass's share; the last pass divides by Z_H
 #pragma unroll
     for (int j = 0; j < aux::MAXCH; j++)
-      if (j < nch) p.out[(size_t)j * p.size + i] = gl::mul(E.total[j], zhi);
+      if (j < nch) {
+        u64 v = E.total[j];
+        u64* o = p.out + (size_t)j * p.size + i;
+        if (PASS > 0) v = gl::add(*o, v);
+        if (PASS == NPASS - 1) v = gl::mul(v, p.zh_inv[i & 1]);
+        *o = v;
+      }
   }
 };
 
