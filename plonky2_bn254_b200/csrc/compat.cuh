@@ -51,6 +51,10 @@ static inline void pb_launch(const char*, F f, size_t n, pbStream, int = 256) {
 #pragma omp parallel for schedule(static)
   for (size_t gid = 0; gid < n; gid++) f(gid);
 }
+template <int THREADS, int MINB, class F>
+static inline void pb_launch_lb(const char* name, F f, size_t n, pbStream s) {
+  pb_launch(name, f, n, s);
+}
 #else
 // ------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
@@ -98,6 +102,20 @@ template <class F>
 __global__ void pb_kernel(F f, size_t n) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid < n) f(gid);
+}
+// Same with a register budget: at least MINB resident CTAs of THREADS threads per SM.
+template <class F, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) pb_kernel_lb(F f, size_t n) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < n) f(gid);
+}
+template <int THREADS, int MINB, class F>
+static inline void pb_launch_lb(const char* name, F f, size_t n, pbStream s) {
+  if (n == 0) return;
+  size_t grid = (n + THREADS - 1) / THREADS;
+  pb_kernel_lb<F, THREADS, MINB><<<(unsigned)grid, THREADS, 0, s>>>(f, n);
+  g_pb_launches++;
+  pb_check_last(name);
 }
 // One thread per work item; functor passed by value. `name` only documents the call site.
 template <class F>
