@@ -51,7 +51,7 @@ static inline void pb_launch(const char*, F f, size_t n, pbStream, int = 256) {
 #pragma omp parallel for schedule(static)
   for (size_t gid = 0; gid < n; gid++) f(gid);
 }
-template <int THREADS, int MINB, class F>
+template <int THREADS, int MIN_CTAS, class F>
 static inline void pb_launch_lb(const char* name, F f, size_t n, pbStream s) {
   pb_launch(name, f, n, s);
 }
@@ -103,17 +103,17 @@ __global__ void pb_kernel(F f, size_t n) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid < n) f(gid);
 }
-// Same with a register budget: at least MINB resident CTAs of THREADS threads per SM.
-template <class F, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) pb_kernel_lb(F f, size_t n) {
+// Same with a register budget: at least MIN_CTAS resident CTAs of THREADS threads per SM.
+template <class F, int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) pb_kernel_lb(F f, size_t n) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid < n) f(gid);
 }
-template <int THREADS, int MINB, class F>
+template <int THREADS, int MIN_CTAS, class F>
 static inline void pb_launch_lb(const char* name, F f, size_t n, pbStream s) {
   if (n == 0) return;
   size_t grid = (n + THREADS - 1) / THREADS;
-  pb_kernel_lb<F, THREADS, MINB><<<(unsigned)grid, THREADS, 0, s>>>(f, n);
+  pb_kernel_lb<F, THREADS, MIN_CTAS><<<(unsigned)grid, THREADS, 0, s>>>(f, n);
   g_pb_launches++;
   pb_check_last(name);
 }

@@ -124,7 +124,23 @@ static __constant__ __align__(16) u64 RC2_DEV[RC2_WORDS] = {
 
 namespace lazy {
 
-__device__ __forceinline__ u64 mul(u64 a, u64 b) { return gl::mul_lazy(a, b); }
+// gl::mul_lazy with the final wrap correction w (2^32 - 1), w in {-1, 0, 1}, built on the ALU pipe
+// (((w >> 1) << 32) | (u32)(-w)) instead of an IMAD.WIDE: in this kernel the FMA pipe is the bottleneck
+// (85 % busy against 64 % for the ALU pipe, profiles/r1_kernels_final.md).
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  const u64 P = gl::mulw32(a0, b0), Q = gl::mulw32(a0, b1), R = gl::mulw32(a1, b0), S = gl::mulw32(a1, b1);
+  const unsigned __int128 prod =
+      (unsigned __int128)P + (((unsigned __int128)Q + R) << 32) + ((unsigned __int128)S << 64);
+  const u64 lo = (u64)prod, hi = (u64)(prod >> 64);
+  const u32 x2 = (u32)hi, x3 = (u32)(hi >> 32);
+  const __int128 V = (__int128)lo - x3 - x2 + ((__int128)x2 << 32);
+  const u64 r = (u64)V;
+  const int w = (int)(long long)(V >> 64);
+  u32 adj_lo, adj_hi;
+  asm("neg.s32 %0, %2;\n\tshr.s32 %1, %2, 1;" : "=r"(adj_lo), "=r"(adj_hi) : "r"(w));
+  return r + (((u64)adj_hi << 32) | adj_lo);
+}
 
 __device__ __forceinline__ u64 sbox(u64 x) {
   const u64 x2 = mul(x, x), x4 = mul(x2, x2), x3 = mul(x, x2);

@@ -13,7 +13,14 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
   __int128 V = (__int128)lo - x3 - x2 + ((__int128)x2 << 32);
   const u64 r = (u64)V;
   const long long w = (long long)(V >> 64);
+#ifdef ADJ_ALU
+  // w in {-1, 0, 1}: w (2^32 - 1) = ((w >> 1) << 32) | (u32)(-w), built on the ALU pipe (the FMA pipe is the bottleneck)
+  u32 adj_lo, adj_hi;
+  asm("neg.s32 %0, %2;\n\tshr.s32 %1, %2, 1;" : "=r"(adj_lo), "=r"(adj_hi) : "r"((int)w));
+  return r + (((u64)adj_hi << 32) | adj_lo);
+#else
   return r + (u64)(w * 0xFFFFFFFFLL);
+#endif
 }
 #else
 __device__ __forceinline__ u64 mul(u64 a, u64 b) {
