@@ -322,7 +322,7 @@ def run_ours(args, rank, world, local_rank):
         "peak_source": peak_src, "algorithmic_bytes_per_launch": lead_bytes, "ms_per_launch": lead_ms,
         "share_of_step": lead_ms / (dev_s / args.steps * 1e3),
         # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, profiles/r1_leafhash_final.txt
-        "traffic": 6.66e9 if (args.instances == 1024) else None,
+        "traffic": 6.70e9 if (args.instances == 1024) else None,
         "poseidon_permutations_per_launch": lead_perms,
         "poseidon_gperm_per_s": lead_perms / (lead_ms * 1e-3) / 1e9 if lead_ms > 0 else 0.0,
         "int_pipe": {

@@ -245,13 +245,17 @@ static inline unsigned fused_threads(int Cp) {  // one radix-8 item per thread i
   int t = Cp >> 3;
   return t >= 512 ? 512u : t >= 64 ? (unsigned)t : 64u;
 }
-static bool g_ntt_attr_set = false;
+// cudaFuncSetAttribute is per device: remember which devices of this process have been configured
+static bool g_ntt_attr_set[64] = {};
 static inline void set_smem_attrs() {
-  if (g_ntt_attr_set) return;
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 63;
+  if (g_ntt_attr_set[dev]) return;
   PB_CUDA(cudaFuncSetAttribute(k_ntt_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PB_CUDA(cudaFuncSetAttribute(k_ntt_pass_d, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PB_CUDA(cudaFuncSetAttribute(k_ntt_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  g_ntt_attr_set = true;
+  g_ntt_attr_set[dev] = true;
 }
 #else
 // ---- hostsim stand-ins: the same mathematical transforms with a plain radix-2 NTT -------------

@@ -1004,10 +1004,13 @@ void generate(Arena& ar, int kind, const u64* d_inputs, const u64* d_ts, size_t 
   if (used > 0) pb_launch("range histogram", HistK{d_trace, freq, n_rows, l.rc_lo, l.rc_hi, d_err}, used, s, 128);
 #else
   if (used > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // per device
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (!attr_set[dev]) {
       PB_CUDA(cudaFuncSetAttribute(k_range_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-      attr_set = true;
+      attr_set[dev] = true;
     }
     size_t bx = (used + 1023) / 1024;
     if (bx > 74) bx = 74;  // 2 halves x 74 = one CTA per SM

@@ -110,3 +110,18 @@ def test_results_are_the_native_outputs(gpu_ctx, oracle, kind, k):
     res = gpu_ctx.prove(kind, inp, ts).results().reshape(k, -1)
     for i in range(k):
         assert (res[i] == oracle.native_result(kind, inp[i])).all()
+
+
+def test_second_device_in_the_same_process(gpu_ctx):
+    """One context per GPU; two contexts on different devices in one process give the same proof
+    (per-device kernel attributes, arena and tables). Skipped on single-GPU boxes."""
+    import torch
+    from plonky2_bn254_b200 import ffi
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    inp, ts = I.make_inputs(I.KIND_FQ, 2, I.config_seed(95))
+    a = gpu_ctx.prove(I.KIND_FQ, inp, ts).words()
+    ctx1 = ffi.Context(1)
+    b = ctx1.prove(I.KIND_FQ, inp, ts).words()
+    ctx1.close()
+    assert (a == b).all()
