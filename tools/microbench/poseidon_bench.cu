@@ -177,6 +177,16 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
 #pragma unroll 1
     for (int r4 = 0; r4 < 4; r4++) {
       const int r = phase * 26 + r4;
+#ifdef SBOX6
+#pragma unroll 1
+      for (int j = 0; j < 2; j++) {
+        u64 t[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) t[i] = sbox(s[i]);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { s[i] = s[i + 6]; s[i + 6] = t[i]; }
+      }
+#else
 #ifdef UNROLL_SBOX
 #pragma unroll
 #else
@@ -188,6 +198,7 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
         for (int i = 0; i < 9; i++) s[i] = s[i + 3];
         s[9] = t0; s[10] = t1; s[11] = t2;
       }
+#endif
       mds_rc(s, rc2 + (r + 1) * 24);
     }
     if (phase == 0) {
