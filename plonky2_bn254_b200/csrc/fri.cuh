@@ -52,7 +52,7 @@ struct PowTableK {  // pw[i] = zeta^i
   E2 zeta;
   PB_HD void operator()(size_t i) const { pw[i] = gl::epow(zeta, (u64)i); }
 };
-static constexpr int PARTS = 256;
+static constexpr int PARTS = 1024;  // row partitions per column: W x PARTS / 256 CTAs, several waves on 148 SMs
 // partial[col][part] = { sum v w[i], sum v w[i-1] } over rows i = part (mod PARTS)
 struct WeightedPartialK {
   const u64* vals;
