@@ -39,9 +39,14 @@ static inline Plan make_plan(int L, int r) {
   p.Kc = forced > 0 ? forced : (L - 10 > 9 ? L - 10 : 9);
   if (p.Kc > L) p.Kc = L;
   if (p.Kc + r > 13) p.Kc = 13 - r;
+  // the fused kernel keeps 2^Kc + 2^(Kc+r) padded words and both twiddle tables in shared memory (<= 200 KB)
+  while (p.Kc > 3 && ((size_t)(17 << p.Kc) / 16 + (size_t)(17 << (p.Kc + r)) / 16 + 32 + (3 << (p.Kc + r)) / 2) * 8 > 200 * 1024)
+    p.Kc--;
   if (L - p.Kc > K1_MAX) p.Kc = L - K1_MAX;
   p.K1 = L - p.Kc;
-  if (p.Kc + r > 13 || L + r > LOG_M) throw Pb254Error(6, "ntt: size not supported");
+  if (p.Kc + r > 13 || L + r > LOG_M ||
+      ((size_t)(17 << p.Kc) / 16 + (size_t)(17 << (p.Kc + r)) / 16 + 32 + (3 << (p.Kc + r)) / 2) * 8 > 200 * 1024)
+    throw Pb254Error(6, "ntt: size not supported");
   return p;
 }
 

@@ -22,7 +22,7 @@ def test_poseidon_permute_matches_oracle_and_kats(gpu_ctx, oracle):
 
 
 @pytest.mark.parametrize("cols,log_n,rate_bits", [(3, 3, 1), (5, 8, 1), (4, 10, 1), (7, 12, 1), (2, 14, 2),
-                                                   (9, 16, 1), (3, 12, 3), (2, 19, 1), (1, 21, 1)])
+                                                   (9, 16, 1), (3, 12, 3), (2, 19, 1), (1, 21, 1), (1, 22, 1), (1, 21, 2)])
 def test_lde_matches_oracle(gpu_ctx, oracle, cols, log_n, rate_bits):
     rng = np.random.default_rng(log_n * 10 + rate_bits)
     v = rand_field(rng, (cols, 1 << log_n))
