@@ -470,9 +470,11 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     pk.pow_bits = (int)cfg.pow_bits;
     u64* d_res = ar.alloc_n<u64>(1);
     pk.result = d_res;
-    const size_t chunk = (size_t)1 << 20;
+    // candidates are tried in increasing order, chunk by chunk (the minimum of the first successful chunk is the
+    // minimal witness); a first chunk of 2^(pow_bits + 1) succeeds with probability 1 - e^-2
+    size_t chunk = (size_t)2 << (cfg.pow_bits < 19 ? cfg.pow_bits : 19);
     u64 found = ~(u64)0;
-    for (u64 base = 0; found == ~(u64)0; base += chunk) {
+    for (u64 base = 0; found == ~(u64)0; base += chunk, chunk = (size_t)1 << 20) {
       if (base >= ((u64)1 << 44)) throw Pb254Error(PB254_E_BAD_ARG, "proof of work search failed");
       pb_memset(d_res, 0xff, 8, s);
       pk.base = base;
