@@ -67,13 +67,24 @@ PB_HD u64 reduce_split(u64 lo, u64 hi) {
 
 PB_HD void mds(u64 s[12]) {
   // MDS_MATRIX_CIRC = [17,15,41,16,2,28,13,13,39,18,34,20], MDS_MATRIX_DIAG = [8,0,...]
+  constexpr u64 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+#if !defined(__CUDA_ARCH__)
+  // host (Fiat-Shamir transcript: ~700 permutations per proof on the critical path): 128-bit accumulation,
+  // one reduction per lane
+  u64 t[24];
+  for (int i = 0; i < 12; i++) t[i] = t[i + 12] = s[i];
+  for (int r = 0; r < 12; r++) {
+    u128 acc = r == 0 ? (u128)t[0] * 8 : (u128)0;
+    for (int i = 0; i < 12; i++) acc += (u128)t[i + r] * C[i];
+    s[r] = gl::reduce128((u64)acc, (u64)(acc >> 64));
+  }
+#else
   u64 lo[12], hi[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     lo[i] = s[i] & gl::EPS;
     hi[i] = s[i] >> 32;
   }
-  constexpr u64 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 #pragma unroll
   for (int r = 0; r < 12; r++) {
     u64 al = 0, ah = 0;
@@ -88,6 +99,7 @@ PB_HD void mds(u64 s[12]) {
     }
     s[r] = reduce_split(al, ah);
   }
+#endif
 }
 
 PB_HD void permute_generic(u64 s[12]) {

@@ -306,17 +306,23 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     E2* d_op = ar.alloc_n<E2>(2 * WA);
     const E2 scale = gl::emul_base(gl::esub(zeta_pow_n, gl::e2(1, 0)), gl::inv((u64)n % gl::P));
     pb_launch("bary weights", fri::BaryWeightsK{wz, zeta, c->tables.t, L}, n, s, 128);
+    // The transcript absorbs [local | aux | quotient], [next | aux_next], [ctl_zs_first]; every batch of opened
+    // values is hashed on the host while the GPU evaluates the next one (the observe ORDER is unchanged).
+    E2* d_op2 = ar.alloc_n<E2>(2 * WA);
     pb_launch("open trace", fri::WeightedPartialK{d_trace, n, n, wz, partial, 1}, (size_t)W * fri::PARTS, s, 256);
     pb_launch("open trace fin", fri::WeightedFinalK{partial, scale, d_op, d_op + W}, W, s, 64);
     pb_d2h(op_tr.data(), d_op, (size_t)W * 32, s);
     pb_sync(s);
     pb_launch("open aux", fri::WeightedPartialK{aux_vals, n, n, wz, partial, 1}, (size_t)A * fri::PARTS, s, 256);
-    pb_launch("open aux fin", fri::WeightedFinalK{partial, scale, d_op, d_op + A}, A, s, 64);
-    pb_d2h(op_ax.data(), d_op, (size_t)A * 32, s);
+    pb_launch("open aux fin", fri::WeightedFinalK{partial, scale, d_op2, d_op2 + A}, A, s, 64);
+    // (host hashing comes before the copy: a device-to-host copy into pageable memory blocks the host)
+    ch.observe_n(op_tr.data(), 2 * (size_t)W);  // local trace values, overlapped with the auxiliary openings
+    pb_d2h(op_ax.data(), d_op2, (size_t)A * 32, s);
     pb_sync(s);
     pb_launch("zeta powers", fri::PowTableK{wz, zeta}, n, s, 128);
     pb_launch("open quotient", fri::WeightedPartialK{qcoef, n, n, wz, partial, 0}, (size_t)Q * fri::PARTS, s, 256);
     pb_launch("open quotient fin", fri::WeightedFinalK{partial, gl::e2(1, 0), d_op, nullptr}, Q, s, 64);
+    ch.observe_n(op_ax.data(), 2 * (size_t)A);  // local auxiliary values, overlapped with the quotient openings
     pb_d2h(op_q.data(), d_op, (size_t)Q * 16, s);
     for (int k = 0; k < 2 * nch; k++) pb_d2h(&zs_first[k], aux_vals + (size_t)(nlk + k) * n, 8, s);
     pb_sync(s);
@@ -327,9 +333,7 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   blob.insert(blob.end(), op_ax.begin(), op_ax.end());
   blob.insert(blob.end(), zs_first.begin(), zs_first.end());
   blob.insert(blob.end(), op_q.begin(), op_q.end());
-  // observe_openings: [local | aux | quotient], [next | aux_next], [ctl_zs_first]
-  ch.observe_n(op_tr.data(), 2 * (size_t)W);
-  ch.observe_n(op_ax.data(), 2 * (size_t)A);
+  // observe_openings, continued: quotient, then [next | aux_next], [ctl_zs_first]
   ch.observe_n(op_q.data(), 2 * (size_t)Q);
   ch.observe_n(op_tr.data() + 2 * W, 2 * (size_t)W);
   ch.observe_n(op_ax.data() + 2 * A, 2 * (size_t)A);
