@@ -240,13 +240,15 @@ __device__ __forceinline__ void permute(u64 s[12], const u64* rc2) {
     for (int r4 = 0; r4 < HALF_FULL; r4++) {
       const int r = phase * (HALF_FULL + N_PARTIAL) + r4;
 #pragma unroll 1
-      for (int j = 0; j < 4; j++) {
-        const u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]);
+      for (int j = 0; j < 2; j++) {  // six lanes per iteration, then the two halves swap places
+        u64 t[6];
 #pragma unroll
-        for (int i = 0; i < 9; i++) s[i] = s[i + 3];
-        s[9] = t0;
-        s[10] = t1;
-        s[11] = t2;
+        for (int i = 0; i < 6; i++) t[i] = sbox(s[i]);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          s[i] = s[i + 6];
+          s[i + 6] = t[i];
+        }
       }
       mds_rc(s, rc2 + (r + 1) * 24);
     }
