@@ -13,6 +13,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <atomic>
 
 typedef uint64_t u64;
 typedef uint32_t u32;
@@ -45,7 +46,7 @@ static inline void pb_memset(void* d, int v, size_t n, pbStream) { memset(d, v, 
 static inline void pb_sync(pbStream) {}
 static inline void pb_set_device(int) {}
 
-extern unsigned long long g_pb_launches;
+extern std::atomic<unsigned long long> g_pb_launches;
 template <class F>
 static inline void pb_launch(const char*, F f, size_t n, pbStream, int = 256) {
 #pragma omp parallel for schedule(static)
@@ -96,7 +97,7 @@ static inline void pb_sync(pbStream s) { PB_CUDA(cudaStreamSynchronize(s)); }
 static inline void pb_set_device(int d) { PB_CUDA(cudaSetDevice(d)); }
 
 // launch counter (reported by bench.py as gpu_launches)
-extern unsigned long long g_pb_launches;
+extern std::atomic<unsigned long long> g_pb_launches;
 
 template <class F>
 __global__ void pb_kernel(F f, size_t n) {

@@ -4,7 +4,7 @@
 // (or, test-only, g++ -x c++ -DPB254_HOSTSIM for the host-simulation library under tests/hostsim/).
 #include "../../include/pb254.h"
 #include "compat.cuh"
-unsigned long long g_pb_launches = 0;
+std::atomic<unsigned long long> g_pb_launches{0};
 #include "context.cuh"
 #include "ntt.cuh"
 #include "merkle.cuh"
@@ -98,7 +98,7 @@ void pb254_config_standard_fast(pb254_config* c) {
 }
 
 const char* pb254_last_error(void) { return g_last_error.c_str(); }
-uint64_t pb254_launch_count(void) { return g_pb_launches; }
+uint64_t pb254_launch_count(void) { return g_pb_launches.load(); }
 
 int pb254_ctx_create(int device, void* stream, pb254_ctx** out) {
   return guarded([&] {

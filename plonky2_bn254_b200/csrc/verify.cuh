@@ -352,9 +352,13 @@ static inline void ctl_tuples(int kind, const u64* inputs, const u64* ts, size_t
   const tg::Layout l = tg::layout_for(kind);
   tuples[0].assign(K, {});
   tuples[1].assign(K, {});
+  // an exception must not leave an OpenMP region (hostsim build): remember the first one and rethrow afterwards
+  int err_code = 0;
+  std::string err_msg;
 #pragma omp parallel for schedule(dynamic, 4)
   for (long long kk = 0; kk < (long long)K; kk++) {
     const size_t k = (size_t)kk;
+    try {
     const u64* w = inputs + k * l.in_words;
     std::vector<u64>&in = tuples[0][k], &out = tuples[1][k];
     if (kind == 2) {
@@ -386,7 +390,15 @@ static inline void ctl_tuples(int kind, const u64* inputs, const u64* ts, size_t
     push_limbs(in, w);  // s as 16 limbs
     in.push_back(ts[k] % gl::P);
     out.push_back(ts[k] % gl::P);
+    } catch (const Pb254Error& e) {
+#pragma omp critical
+      if (!err_code) {
+        err_code = e.code;
+        err_msg = e.what();
+      }
+    }
   }
+  if (err_code) throw Pb254Error(err_code, err_msg);
 }
 
 // ---- Merkle ------------------------------------------------------------------------------------------

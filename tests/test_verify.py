@@ -56,3 +56,13 @@ def test_accepts_oracle_g1_proof_and_native_results(hs_lib, oracle):
     bad[1, 0] ^= np.uint64(1)
     with pytest.raises(ffi.Pb254Error):
         hs_lib.verify(pf.words(), bad, ts)
+
+
+def test_non_canonical_public_input_is_an_error_not_a_crash(hs_lib, fq_case):
+    """x >= p in the batch handed to the verifier: PB254_E_NOT_CANONICAL (raised inside the parallel native-result
+    loop of the hostsim build, which must not let an exception escape an OpenMP region)."""
+    inp = fq_case["inputs"].copy()
+    inp[1, 4:8] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with pytest.raises(ffi.Pb254Error) as e:
+        hs_lib.verify(fq_case["words"], inp, fq_case["timestamps"])
+    assert e.value.code == 3
