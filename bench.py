@@ -322,15 +322,15 @@ def run_ours(args, rank, world, local_rank):
         "peak_source": peak_src, "algorithmic_bytes_per_launch": lead_bytes, "ms_per_launch": lead_ms,
         "share_of_step": lead_ms / (dev_s / args.steps * 1e3),
         # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, profiles/r1_leafhash_final.txt
-        "traffic": 6.70e9 if (args.instances == 1024) else None,
+        "traffic": 6.66e9 if (args.instances == 1024) else None,
         "poseidon_permutations_per_launch": lead_perms,
         "poseidon_gperm_per_s": lead_perms / (lead_ms * 1e-3) / 1e9 if lead_ms > 0 else 0.0,
         "int_pipe": {
-            "thread_instructions_per_permutation": 25.2e3,
-            "issue_peak_gperm_per_s": 148 * 128 * 1.965e9 / 25.2e3 / 1e9,
-            "fma_heavy_pipe_busy": 0.84, "alu_pipe_busy": 0.68, "issue_active": 0.73,
-            "note": "ncu (profiles/r1_kernels_final.md): the FMA-heavy pipe (IMAD / IDP) is 84 % busy, issue slots "
-                    "73 %; the kernel is bound by the integer pipes, not by HBM"},
+            "thread_instructions_per_permutation": 24.5e3,
+            "issue_peak_gperm_per_s": 148 * 128 * 1.965e9 / 24.5e3 / 1e9,
+            "fma_heavy_pipe_busy": 0.85, "alu_pipe_busy": 0.65, "issue_active": 0.72,
+            "note": "ncu (profiles/r1_kernels_final.md): the FMA-heavy pipe (IMAD / IDP) is 85 % busy, issue slots "
+                    "72 %; the kernel is bound by the integer pipes, not by HBM"},
         "all_trees": {"algorithmic_bytes_per_proof": merkle_bytes, "ms_per_proof": merkle_ms,
                       "achieved_gb_s": merkle_bytes / (merkle_ms * 1e-3) / 1e9 if merkle_ms > 0 else 0.0,
                       "poseidon_permutations_per_proof": leaf_perms},
