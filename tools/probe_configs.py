@@ -1,4 +1,4 @@
-"""GPU probe: BASELINE configs 3 and 4 at full size (G2 x 2^10; fq_exp x 2^12 with blow-up 2 and 8),
+"""GPU probe: BASELINE configs 1-4 at full size (G2 x 2^10; fq_exp x 2^12 with blow-up 2 and 8),
 verified by the product's host verifier."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,7 +6,8 @@ import numpy as np
 from plonky2_bn254_b200 import ffi, inputs as I
 
 ctx = ffi.Context(0)
-cases = [("config 3: G2 x 1024", 1, 1024, None), ("config 4a: fq_exp x 4096, rate_bits 1", 2, 4096, None),
+cases = [("config 1: G1 x 1 (512 rows)", 0, 1, None), ("config 2: G1 x 1024", 0, 1024, None),
+         ("config 3: G2 x 1024", 1, 1024, None), ("config 4a: fq_exp x 4096, rate_bits 1", 2, 4096, None),
          ("config 4b: fq_exp x 4096, rate_bits 3, 28 queries", 2, 4096, (3, 28))]
 for name, kind, k, rb in cases:
     t = time.time(); inp, ts = I.make_inputs(kind, k, I.config_seed(3 + kind)); tgen = time.time() - t
