@@ -6,7 +6,7 @@ import numpy as np
 from plonky2_bn254_b200 import ffi, inputs as I
 
 ctx = ffi.Context(0)
-cases = [("config 1: G1 x 1 (512 rows)", 0, 1, None), ("config 2: G1 x 1024", 0, 1024, None),
+cases = [("config 1: G1 x 1 (2^16 rows = min_rows)", 0, 1, None), ("config 2: G1 x 1024", 0, 1024, None),
          ("config 3: G2 x 1024", 1, 1024, None), ("config 4a: fq_exp x 4096, rate_bits 1", 2, 4096, None),
          ("config 4b: fq_exp x 4096, rate_bits 3, 28 queries", 2, 4096, (3, 28))]
 for name, kind, k, rb in cases:
