@@ -38,7 +38,9 @@ enum {
   PB254_E_CUDA = 4,          /* CUDA runtime failure */
   PB254_E_OOM = 5,           /* device allocation failure */
   PB254_E_BAD_ARG = 6,
-  PB254_E_VERIFY = 7         /* verifier.rs: proof rejected */
+  PB254_E_VERIFY = 7,        /* verifier.rs: proof rejected */
+  PB254_E_NOT_ON_CURVE = 8   /* an input point is not on the curve: G1Affine / G2Affine are curve points by construction
+                                in the reference (ark-ec); the device chains re-associate additions and need the group law */
 };
 
 /* StarkConfig (starky config.rs; the reference hard-wires standard_fast_config() at
@@ -130,12 +132,15 @@ void pb254_proof_free(pb254_proof* proof);
 
 /* ---- verification (host; the reference verifies on the CPU as well) ----------------------------- */
 /* verify(stark, config, ctls, proof, public_inputs = [], extra_looking_values)
- * (src/starks/common/verifier.rs:32-98) on a serialized proof. The extra looking values are recomputed
- * natively from the batch (inputs / timestamps, same wire format as pb254_prove), as run_once does with
+ * (src/starks/common/verifier.rs:32-98) on a serialized proof. As in the reference, the STARK (`kind`) and the
+ * StarkConfig (`cfg`, NULL = standard_fast_config) are the CALLER's: a proof whose header names another kind or
+ * other parameters (fewer query rounds, no grinding, ...) is rejected; only degree_bits is taken from the proof.
+ * `inputs` holds n_inputs rows of pb254_input_words(kind) words. The extra looking values are recomputed natively
+ * from the batch (inputs / timestamps, same wire format as pb254_prove), as run_once does with
  * g1_generate_ctl_values (src/starks/curves/g1/scalar_mul_ctl.rs:57-80). Returns PB254_OK or PB254_E_VERIFY
  * (pb254_last_error() names the failed check). Needs no context and no GPU. */
-int pb254_verify(const uint64_t* proof_words, size_t n_words, const uint64_t* inputs, const uint64_t* timestamps,
-                 size_t n_inputs);
+int pb254_verify(int kind, const pb254_config* cfg, const uint64_t* proof_words, size_t n_words,
+                 const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs);
 /* Serialized StarkProofWithMetadata: little-endian u64 words, field order of SURVEY.md C.7 behind a
  * 10-word header {magic, kind, degree_bits, config[7]} (layout in DESIGN.md). */
 size_t pb254_proof_words(const pb254_proof* proof);

@@ -190,6 +190,51 @@ int orc_commit(const u64* values, size_t cols, size_t n, unsigned rate_bits, uns
     return fail(e);
   }
 }
+// Same commitment as orc_commit (from_values), evaluated in column chunks of SPONGE_RATE so that only one chunk of
+// the LDE and one sponge state per row are alive: the cap of a matrix whose LDE does not fit in host memory
+// (BASELINE config 4: 427 columns x 2^24 LDE rows). hash_no_pad absorbs 8 elements per permutation, so the state of
+// row j after chunk c equals the state of the one-shot hash after the same 8 (c + 1) elements.
+int orc_commit_streamed(const u64* values, size_t cols, size_t n, unsigned rate_bits, unsigned cap_height, u64* cap_out) {
+  try {
+    if (cols <= 4) throw OracleError(E_INTERNAL, "streamed commit: rows of <= 4 elements are not hashed");
+    const size_t N = n << rate_bits;
+    const unsigned lg = log2_strict(N);
+    std::vector<u64> state(N * 12, 0);
+    // one chunk = a multiple of SPONGE_RATE columns, at least one column per thread for the LDE phase
+    const size_t per = (size_t)SPONGE_RATE * (((size_t)omp_get_max_threads() + SPONGE_RATE - 1) / SPONGE_RATE);
+    for (size_t c0 = 0; c0 < cols; c0 += per) {
+      const size_t len = cols - c0 < per ? cols - c0 : per;
+      std::vector<std::vector<u64>> lde(len);
+#pragma omp parallel for schedule(dynamic, 1)
+      for (size_t k = 0; k < len; k++)
+        lde[k] = lde_onto_coset(std::vector<u64>(values + (c0 + k) * n, values + (c0 + k + 1) * n), rate_bits);
+#pragma omp parallel for schedule(static)
+      for (size_t j = 0; j < N; j++) {
+        u64* s = &state[j * 12];
+        for (size_t k0 = 0; k0 < len; k0 += SPONGE_RATE) {
+          const size_t m = len - k0 < (size_t)SPONGE_RATE ? len - k0 : (size_t)SPONGE_RATE;
+          for (size_t k = 0; k < m; k++) s[k] = lde[k0 + k][j];
+          poseidon_permute(s);
+        }
+      }
+    }
+    std::vector<Hash4> level(N);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < N; i++) memcpy(level[i].e, &state[reverse_bits(i, lg) * 12], 32);
+    std::vector<u64>().swap(state);
+    for (unsigned l = 0; l < lg - cap_height; l++) {
+      size_t m = level.size() / 2;
+      std::vector<Hash4> nxt(m);
+#pragma omp parallel for schedule(static)
+      for (size_t i = 0; i < m; i++) nxt[i] = two_to_one(level[2 * i], level[2 * i + 1]);
+      level.swap(nxt);
+    }
+    memcpy(cap_out, level.data(), level.size() * 32);
+    return 0;
+  } catch (OracleError& e) {
+    return fail(e);
+  }
+}
 // Merkle tree over given row-major leaves
 int orc_merkle(const u64* leaves, size_t num_leaves, size_t leaf_len, unsigned cap_height, u64* cap_out) {
   MerkleTree t;

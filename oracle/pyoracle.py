@@ -142,6 +142,16 @@ def commit(values, rate_bits, cap_height, from_coeffs=False, want_digests=False)
     return (cap, dig) if want_digests else cap
 
 
+def commit_streamed(values, rate_bits, cap_height):
+    """Cap of PolynomialBatch::from_values, computed in 8-column chunks (bounded host memory)."""
+    values = _u64(values)
+    cols, n = values.shape
+    cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+    _check(lib().orc_commit_streamed(_p(values), C.c_size_t(cols), C.c_size_t(n), C.c_uint(rate_bits),
+                                     C.c_uint(cap_height), _p(cap)))
+    return cap
+
+
 def merkle_cap(leaves, cap_height):
     leaves = _u64(leaves)
     n, w = leaves.shape

@@ -36,6 +36,19 @@ struct InvTableK {  // invt[j][v] = 1 / (v + beta_j)
   }
 };
 
+// pb254_prove_trace only: the cells a generated trace has range-checked by construction (one thread per row)
+struct RangePrecheckK {
+  const u64* trace;
+  size_t n;
+  int rc_lo, rc_hi, table_col;
+  int* err;
+  PB_HD void operator()(size_t i) const {
+    u64 bad = trace[(size_t)table_col * n + i] >> 16;
+    for (int c = rc_lo; c < rc_hi; c++) bad |= trace[(size_t)c * n + i] >> 16;
+    if (bad) *err = 1;
+  }
+};
+
 struct HelpersK {  // one thread per row
   const u64* trace;
   u64* auxm;       // A x n

@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <string>
 #include <atomic>
+#include <mutex>
 
 typedef uint64_t u64;
 typedef uint32_t u32;

@@ -9,11 +9,11 @@
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, off = 0, high = 0;
-  // Allocation failing to fit means the reservation was too small: a programming error here, the
-  // caller sizes the arena from the proof shape before the first kernel is launched.
+  // The caller sizes the arena from the proof shape before the first kernel is launched; not fitting is reported
+  // as PB254_E_OOM like a failed cudaMalloc of the reservation itself.
   void* alloc(size_t bytes) {
     size_t a = (off + 255) & ~(size_t)255;
-    if (a + bytes > cap) throw Pb254Error(5, "device workspace exhausted (reserve() too small)");
+    if (a + bytes > cap) throw Pb254Error(5 /* PB254_E_OOM */, "device workspace exhausted");
     off = a + bytes;
     if (off > high) high = off;
     return base + a;
@@ -86,6 +86,15 @@ struct StageTimes {
     if (id < 0) return;
 #if !PB_HOSTSIM
     PB_CUDA(cudaEventRecord(recs[id].b, s));
+#else
+    (void)s;
+    recs[id].ms = now() - recs[id].t0;
+#endif
+  }
+  void end_nothrow(int id, pbStream s) noexcept {
+    if (id < 0) return;
+#if !PB_HOSTSIM
+    (void)cudaEventRecord(recs[id].b, s);  // an error here is sticky and is reported by the next pb_sync
 #else
     (void)s;
     recs[id].ms = now() - recs[id].t0;

@@ -251,11 +251,14 @@ static inline unsigned fused_threads(int Cp) {  // one radix-8 item per thread i
   return t >= 512 ? 512u : t >= 64 ? (unsigned)t : 64u;
 }
 // cudaFuncSetAttribute is per device: remember which devices of this process have been configured
+// (contexts on different devices are created and used from different threads: the table is guarded)
 static bool g_ntt_attr_set[64] = {};
+static std::mutex g_ntt_attr_mutex;
 static inline void set_smem_attrs() {
   int dev = 0;
   PB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) dev = 63;
+  std::lock_guard<std::mutex> lock(g_ntt_attr_mutex);
   if (g_ntt_attr_set[dev]) return;
   PB_CUDA(cudaFuncSetAttribute(k_ntt_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   PB_CUDA(cudaFuncSetAttribute(k_ntt_pass_d, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

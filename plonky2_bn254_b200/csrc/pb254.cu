@@ -41,6 +41,30 @@ int ilog2_strict(size_t n) {
   return k;
 }
 
+// One argument check for every extern "C" entry: never dereference before these pass (PB254_E_BAD_ARG).
+void need(bool ok, const char* what) {
+  if (!ok) throw Pb254Error(PB254_E_BAD_ARG, what);
+}
+void need_ctx(const pb254_ctx* c) { need(c != nullptr, "null context"); }
+void need_kind(int kind) { need(kind >= 0 && kind <= 2, "unknown STARK kind (0 = G1, 1 = G2, 2 = Fq)"); }
+// trace heights: a power of two, at least 2^16 (the range-check table needs 65536 rows) and at most 2^26
+int need_trace_rows(size_t n_rows) {
+  int k = 0;
+  while (k < 27 && ((size_t)1 << k) < n_rows) k++;
+  need(((size_t)1 << k) == n_rows && k >= 16 && k <= 26, "trace height must be a power of two in 2^16 .. 2^26");
+  return k;
+}
+pb254_config config_or_default(const pb254_config* cfg_in, int log_rows) {
+  pb254_config cfg;
+  if (cfg_in)
+    cfg = *cfg_in;
+  else
+    pb254_config_standard_fast(&cfg);
+  prover::validate_config(cfg);
+  if (log_rows >= 0) need(cfg.cap_height <= (unsigned)log_rows + cfg.rate_bits, "cap_height larger than log2 of the LDE size");
+  return cfg;
+}
+
 struct Shape {
   int L, width, aux_len, in_words;
 };
@@ -54,6 +78,8 @@ Shape shape_for(int kind) {
 }
 
 void throw_trace_error(int herr) {
+  if (herr == tg::ERR_NOT_ON_CURVE)
+    throw Pb254Error(PB254_E_NOT_ON_CURVE, "an input point is not on the curve (G1: y^2 = x^3 + 3, G2: y^2 = x^3 + 3/(9+u))");
   if (herr == tg::ERR_NOT_CANONICAL) throw Pb254Error(PB254_E_NOT_CANONICAL, "input coordinate >= p");
   if (herr == tg::ERR_INFINITY)
     throw Pb254Error(PB254_E_INFINITY, "an intermediate sum is the point at infinity (a = -b), unsupported by design");
@@ -133,9 +159,13 @@ void pb254_ctx_destroy(pb254_ctx* c) {
 }
 
 /* stage timings of the last call on this context (device time, ms) */
-int pb254_timing_count(pb254_ctx* c) { return (int)c->times.recs.size(); }
-const char* pb254_timing_name(pb254_ctx* c, int i) { return c->times.recs[i].name.c_str(); }
-double pb254_timing_ms(pb254_ctx* c, int i) { return c->times.recs[i].ms; }
+int pb254_timing_count(pb254_ctx* c) { return c ? (int)c->times.recs.size() : 0; }
+const char* pb254_timing_name(pb254_ctx* c, int i) {
+  return c && i >= 0 && i < (int)c->times.recs.size() ? c->times.recs[i].name.c_str() : "";
+}
+double pb254_timing_ms(pb254_ctx* c, int i) {
+  return c && i >= 0 && i < (int)c->times.recs.size() ? c->times.recs[i].ms : 0.0;
+}
 
 int pb254_trace_width(int kind) { return kind >= 0 && kind <= 2 ? shape_for(kind).width : -1; }
 int pb254_input_words(int kind) { return kind >= 0 && kind <= 2 ? shape_for(kind).in_words : -1; }
@@ -153,6 +183,7 @@ size_t pb254_trace_rows(size_t n_inputs, size_t min_rows) {
 
 int pb254_poseidon_permute(pb254_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
   return guarded([&] {
+    need_ctx(c);
     pb_set_device(c->device);
     c->arena.reserve(2 * n * 96 + 1024);
     c->arena.reset();
@@ -168,6 +199,7 @@ int pb254_poseidon_permute(pb254_ctx* c, const uint64_t* in, size_t n, uint64_t*
 int pb254_lde_batch(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits, int from_coeffs,
                     uint64_t* lde_out) {
   return guarded([&] {
+    need_ctx(c);
     pb_set_device(c->device);
     int L = ilog2_strict(n);
     size_t N = n << rate_bits;
@@ -187,6 +219,7 @@ int pb254_lde_batch(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n,
 int pb254_commit(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n, uint32_t rate_bits, uint32_t cap_height,
                  int from_coeffs, uint64_t* cap_out, uint64_t* digests_out) {
   return guarded([&] {
+    need_ctx(c);
     pb_set_device(c->device);
     int L = ilog2_strict(n);
     size_t N = n << rate_bits;
@@ -218,10 +251,13 @@ int pb254_commit(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n, ui
 int pb254_generate_trace(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
                          size_t min_rows, uint64_t* cols_out) {
   return guarded([&] {
+    need_ctx(c);
+    need_kind(kind);
+    need(inputs && timestamps && cols_out && n_inputs > 0, "null or empty argument");
     pb_set_device(c->device);
-    tg::Layout l = tg::layout_for(shape_for(kind).width == 0 ? 0 : kind);
+    tg::Layout l = tg::layout_for(kind);
     size_t n_rows = pb254_trace_rows(n_inputs, min_rows);
-    if (n_rows < 65536) throw Pb254Error(PB254_E_BAD_ARG, "trace must have at least 2^16 rows (range-check table)");
+    need_trace_rows(n_rows);
     size_t tbytes = (size_t)l.width * n_rows * 8;
     c->arena.reserve(tbytes + tg::scratch_bytes(kind, n_inputs) + n_inputs * (l.in_words + 1) * 8 + 65536);
     c->arena.reset();
@@ -251,18 +287,14 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
                              size_t min_rows, const pb254_config* cfg_in, int keep_debug, pb254_proof** out,
                              bool inputs_on_device) {
   return guarded([&] {
-    if (!out) throw Pb254Error(PB254_E_BAD_ARG, "null out pointer");
-    if (!c || !inputs || !timestamps || n_inputs == 0) throw Pb254Error(PB254_E_BAD_ARG, "null or empty input");
+    need(out != nullptr, "null out pointer");
+    need_ctx(c);
+    need_kind(kind);
+    need(inputs && timestamps && n_inputs > 0, "null or empty input");
     pb_set_device(c->device);
-    pb254_config cfg;
-    if (cfg_in)
-      cfg = *cfg_in;
-    else
-      pb254_config_standard_fast(&cfg);
-    prover::validate_config(cfg);
-    tg::Layout l = tg::layout_for(shape_for(kind).width ? kind : 0);
+    tg::Layout l = tg::layout_for(kind);
     size_t n_rows = pb254_trace_rows(n_inputs, min_rows);
-    if (n_rows < 65536) throw Pb254Error(PB254_E_BAD_ARG, "trace must have at least 2^16 rows (range-check table)");
+    const pb254_config cfg = config_or_default(cfg_in, need_trace_rows(n_rows));
     size_t twords = (size_t)l.width * n_rows;
     size_t tg_bytes = tg::scratch_bytes(kind, n_inputs) + n_inputs * (l.in_words + 1) * 8 + 65536;
     size_t pv_bytes = prover::workspace_bytes(kind, n_rows, cfg);
@@ -326,21 +358,33 @@ int pb254_prove_dev(pb254_ctx* c, int kind, const uint64_t* d_inputs, const uint
 int pb254_prove_trace(pb254_ctx* c, int kind, const uint64_t* trace_cols, size_t n_rows, const pb254_config* cfg_in,
                       int keep_debug, pb254_proof** out) {
   return guarded([&] {
-    if (!out) throw Pb254Error(PB254_E_BAD_ARG, "null out pointer");
+    need(out != nullptr, "null out pointer");
+    need_ctx(c);
+    need_kind(kind);
+    need(trace_cols != nullptr, "null trace");
     pb_set_device(c->device);
-    pb254_config cfg;
-    if (cfg_in)
-      cfg = *cfg_in;
-    else
-      pb254_config_standard_fast(&cfg);
-    prover::validate_config(cfg);
-    tg::Layout l = tg::layout_for(shape_for(kind).width ? kind : 0);
+    const pb254_config cfg = config_or_default(cfg_in, need_trace_rows(n_rows));
+    tg::Layout l = tg::layout_for(kind);
     size_t twords = (size_t)l.width * n_rows;
     c->arena.reserve(twords * 8 + prover::workspace_bytes(kind, n_rows, cfg) + 65536);
     c->arena.reset();
     c->times.clear();
     u64* d_trace = c->arena.alloc_n<u64>(twords);
     pb_h2d(d_trace, trace_cols, twords * 8, c->stream);
+    {
+      // A host-supplied trace has not been through generate_range_checks: every looked-up cell and the table column
+      // must be < 2^16 (the reference asserts this while filling the frequency column, g1/scalar_mul_stark.rs:71-87).
+      size_t mark = c->arena.off;
+      int* d_err = c->arena.alloc_n<int>(1);
+      pb_memset(d_err, 0, sizeof(int), c->stream);
+      pb_launch("range pre-check", aux::RangePrecheckK{d_trace, n_rows, l.rc_lo, l.rc_hi, l.range_counter, d_err},
+                n_rows, c->stream, 128);
+      int herr = 0;
+      pb_d2h(&herr, d_err, sizeof(int), c->stream);
+      pb_sync(c->stream);
+      c->arena.off = mark;
+      if (herr) throw Pb254Error(PB254_E_BAD_ARG, "trace: a range-checked cell or the range counter is >= 2^16");
+    }
     pb254_proof* pf = new pb254_proof();
     try {
       prover::prove_device(c, kind, d_trace, n_rows, cfg, pf->data, keep_debug != 0);
@@ -359,6 +403,7 @@ int pb254_prove_trace(pb254_ctx* c, int kind, const uint64_t* trace_cols, size_t
 int pb254_lde_dev(pb254_ctx* c, const uint64_t* d_values, size_t cols, size_t n, uint32_t rate_bits, int from_coeffs,
                   uint64_t* d_lde_out) {
   return guarded([&] {
+    need_ctx(c);
     pb_set_device(c->device);
     int L = ilog2_strict(n);
     c->arena.reserve(cols * n * 8 + 4096);
@@ -377,6 +422,7 @@ int pb254_lde_dev(pb254_ctx* c, const uint64_t* d_values, size_t cols, size_t n,
 int pb254_leaf_hash_rows_dev(pb254_ctx* c, const uint64_t* d_matrix, size_t stride, size_t cols, size_t rows,
                              uint64_t* d_digests_out) {
   return guarded([&] {
+    need_ctx(c);
     pb_set_device(c->device);
     c->times.clear();
     int t0 = c->times.begin("leaf hash rows", c->stream);
@@ -392,6 +438,7 @@ int pb254_leaf_hash_rows_dev(pb254_ctx* c, const uint64_t* d_matrix, size_t stri
 int pb254_merkle_subtree_dev(pb254_ctx* c, const uint64_t* d_all_digests, uint32_t log_total, size_t first,
                              uint32_t log_sub, uint32_t log_roots, uint64_t* d_roots_out) {
   return guarded([&] {
+    need_ctx(c);
     pb_set_device(c->device);
     if (log_roots > log_sub || log_sub > log_total) throw Pb254Error(PB254_E_BAD_ARG, "subtree shape");
     size_t nd = merkle::tree_digests((int)log_sub, (int)log_roots);
@@ -413,11 +460,13 @@ int pb254_merkle_subtree_dev(pb254_ctx* c, const uint64_t* d_all_digests, uint32
 
 // verify(stark, config, ctls, proof, [], extra_looking_values) of src/starks/common/verifier.rs:32-98, with the
 // extra looking values recomputed natively from the batch as run_once does (g1/scalar_mul_ctl.rs:57-80).
-int pb254_verify(const uint64_t* proof_words, size_t n_words, const uint64_t* inputs, const uint64_t* timestamps,
-                 size_t n_inputs) {
+int pb254_verify(int kind, const pb254_config* cfg_in, const uint64_t* proof_words, size_t n_words,
+                 const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs) {
   return guarded([&] {
-    if (!proof_words || !inputs || !timestamps) throw Pb254Error(PB254_E_BAD_ARG, "null argument");
-    verify::verify_proof(proof_words, n_words, inputs, timestamps, n_inputs);
+    need_kind(kind);
+    need(proof_words && inputs && timestamps, "null argument");
+    const pb254_config cfg = config_or_default(cfg_in, -1);
+    verify::verify_proof(kind, cfg, proof_words, n_words, inputs, timestamps, n_inputs);
   });
 }
 

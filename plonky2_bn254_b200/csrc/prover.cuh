@@ -82,6 +82,8 @@ static inline void validate_config(const pb254_config& c) {
   if (c.arity_bits < 1 || c.arity_bits > 4) throw Pb254Error(PB254_E_BAD_ARG, "arity_bits must be in 1..4");
   if (c.pow_bits > 40) throw Pb254Error(PB254_E_BAD_ARG, "pow_bits too large");
   if (c.num_query_rounds < 1 || c.num_query_rounds > 1024) throw Pb254Error(PB254_E_BAD_ARG, "num_query_rounds");
+  if (c.cap_height > 16) throw Pb254Error(PB254_E_BAD_ARG, "cap_height must be <= 16");
+  if (c.final_poly_bits > 16) throw Pb254Error(PB254_E_BAD_ARG, "final_poly_bits must be <= 16");
 }
 
 // device bytes needed by prove_device for an (kind, n, cfg) proof, excluding the trace values
@@ -104,7 +106,9 @@ struct Stage {
   pb254_ctx* c;
   int id;
   Stage(pb254_ctx* c_, const char* name) : c(c_), id(c_->times.begin(name, c_->stream)) {}
-  ~Stage() { c->times.end(id, c->stream); }
+  // a destructor must not throw (a sticky CUDA error, or unwinding from another throw): the failure is recorded
+  // and surfaces at the next synchronisation of the stream
+  ~Stage() { c->times.end_nothrow(id, c->stream); }
 };
 
 // d_trace: W x n column-major device matrix (trace values on H). Fills out.blob.

@@ -199,6 +199,10 @@ struct FieldIO<bn::F1> {
     out = bn::to_mont(bn::from_words(w));
     return true;
   }
+  // y^2 = x^3 + 3
+  static PB_HD bool on_curve(const bn::Aff<bn::F1>& p) {
+    return bn::eq(bn::sqr(p.y), bn::add(bn::mul(bn::sqr(p.x), p.x), bn::small(3)));
+  }
 };
 template <>
 struct FieldIO<bn::F2> {
@@ -208,6 +212,13 @@ struct FieldIO<bn::F2> {
     out.c0 = bn::to_mont(bn::from_words(w));
     out.c1 = bn::to_mont(bn::from_words(w + 4));
     return true;
+  }
+  // y^2 = x^3 + 3 / (9 + u), checked as (9 + u) (y^2 - x^3) = 3
+  static PB_HD bool on_curve(const bn::Aff<bn::F2>& p) {
+    const bn::Fq2 d = bn::F2::sub(bn::F2::sqr(p.y), bn::F2::mul(bn::F2::sqr(p.x), p.x));
+    const bn::Fq nine = bn::small(9);
+    const bn::Fq c0 = bn::sub(bn::mul(nine, d.c0), d.c1), c1 = bn::add(d.c0, bn::mul(nine, d.c1));
+    return bn::eq(c0, bn::small(3)) && bn::is_zero(c1);
   }
 };
 
@@ -248,6 +259,12 @@ struct ChainsK {
               FieldIO<F>::load(w + 4 + 2 * FW, off.x) & FieldIO<F>::load(w + 4 + 3 * FW, off.y);
     if (!ok) {
       set_err(B.err, ERR_NOT_CANONICAL);
+      return;
+    }
+    // G1Affine / G2Affine are points of the curve by construction in the reference; the step-parallel chains below
+    // rely on the group law being associative, which only holds on the curve
+    if (!FieldIO<F>::on_curve(x) || !FieldIO<F>::on_curve(off)) {
+      set_err(B.err, ERR_NOT_ON_CURVE);
       return;
     }
     B.D[k] = x;
@@ -309,6 +326,10 @@ __global__ void __launch_bounds__(32) k_dbl_chain(CurveBufs<F> B, const u64* __r
   if (!ok) {
     set_err(B.err, ERR_NOT_CANONICAL);
     x.x = x.y = off.x = off.y = F::one();  // keep the later kernels well defined; the error word wins
+  } else if (!FieldIO<F>::on_curve(x) || !FieldIO<F>::on_curve(off)) {
+    // the prefix scan of k_sum_scan re-associates the additions: only valid in the curve group
+    set_err(B.err, ERR_NOT_ON_CURVE);
+    x.x = x.y = off.x = off.y = F::one();
   }
   B.D[k] = x;
   B.off[k] = off;
@@ -1005,12 +1026,16 @@ void generate(Arena& ar, int kind, const u64* d_inputs, const u64* d_ts, size_t 
 #else
   if (used > 0) {
     static bool attr_set[64] = {};  // per device
+    static std::mutex attr_mutex;
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) dev = 63;
-    if (!attr_set[dev]) {
-      PB_CUDA(cudaFuncSetAttribute(k_range_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-      attr_set[dev] = true;
+    {
+      std::lock_guard<std::mutex> lock(attr_mutex);
+      if (!attr_set[dev]) {
+        PB_CUDA(cudaFuncSetAttribute(k_range_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+        attr_set[dev] = true;
+      }
     }
     size_t bx = (used + 1023) / 1024;
     if (bx > 74) bx = 74;  // 2 halves x 74 = one CTA per SM

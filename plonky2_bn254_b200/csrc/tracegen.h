@@ -29,7 +29,7 @@ namespace tg {
 
 static constexpr int PERIOD = 512, NBITS = 256;
 // device error word: the maximum wins, so the root cause outranks the inconsistencies it triggers
-static constexpr int ERR_INTERNAL = 1, ERR_INFINITY = 2, ERR_NOT_CANONICAL = 3;
+static constexpr int ERR_INTERNAL = 1, ERR_INFINITY = 2, ERR_NOT_CANONICAL = 3, ERR_NOT_ON_CURVE = 4;
 
 struct Layout {
   int kind, L, aux_len, width;

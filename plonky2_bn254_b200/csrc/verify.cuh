@@ -429,19 +429,22 @@ static inline void check_merkle(const u64* leaf, size_t leaf_len, size_t index, 
 }
 
 // ---- the verifier -------------------------------------------------------------------------------------
-static inline void verify_proof(const u64* blob, size_t words, const u64* inputs, const u64* timestamps, size_t K) {
-  if (words < 22 || blob[0] != prover::PROOF_MAGIC) throw VerifyError("not a pb254 proof blob");
-  const int kind = (int)blob[1], L = (int)blob[2];
-  if (kind < 0 || kind > 2 || L < 8 || L > 26) throw VerifyError("bad header");
-  pb254_config cfg;
-  cfg.rate_bits = (uint32_t)blob[3];
-  cfg.cap_height = (uint32_t)blob[4];
-  cfg.num_challenges = (uint32_t)blob[5];
-  cfg.num_query_rounds = (uint32_t)blob[6];
-  cfg.pow_bits = (uint32_t)blob[7];
-  cfg.arity_bits = (uint32_t)blob[8];
-  cfg.final_poly_bits = (uint32_t)blob[9];
+// `kind` and `cfg` are the CALLER's (the reference's verify(stark, config, ...) takes the StarkConfig from the caller,
+// src/starks/common/verifier.rs:32-45): every security parameter stamped into the blob header must equal them, only
+// degree_bits is read from the proof. `inputs` holds K rows of in_words(kind) words.
+static inline void verify_proof(int kind, const pb254_config& cfg, const u64* blob, size_t words, const u64* inputs,
+                                const u64* timestamps, size_t K) {
+  if (kind < 0 || kind > 2) throw Pb254Error(PB254_E_BAD_ARG, "unknown STARK kind");
   prover::validate_config(cfg);
+  if (words < 22 || blob[0] != prover::PROOF_MAGIC) throw VerifyError("not a pb254 proof blob");
+  if (blob[1] != (u64)kind) throw VerifyError("proof header: STARK kind differs from the caller's");
+  const u64 want[7] = {cfg.rate_bits, cfg.cap_height, cfg.num_challenges, cfg.num_query_rounds,
+                       cfg.pow_bits,  cfg.arity_bits, cfg.final_poly_bits};
+  for (int i = 0; i < 7; i++)
+    if (blob[3 + i] != want[i]) throw VerifyError("proof header: StarkConfig differs from the caller's");
+  if (blob[2] < 16 || blob[2] > 26) throw VerifyError("proof header: degree_bits");
+  const int L = (int)blob[2];
+  if (K > (((size_t)1 << L) >> 9)) throw VerifyError("more public instances than the trace has periods");
   const tg::Layout l = tg::layout_for(kind);
   const int nch = (int)cfg.num_challenges, W = l.width, NH = aux::num_helpers(l), A = aux::num_aux(l, nch), Q = 2 * nch,
             nlk = (NH + 1) * nch, r = (int)cfg.rate_bits, logN = L + r, cap_h = (int)cfg.cap_height;

@@ -18,7 +18,7 @@ KIND_G1, KIND_G2, KIND_FQ = 0, 1, 2
 
 ERROR_NAMES = {
     0: "OK", 1: "E_SCALAR_RANGE", 2: "E_INFINITY", 3: "E_NOT_CANONICAL", 4: "E_CUDA", 5: "E_OOM", 6: "E_BAD_ARG",
-    7: "E_VERIFY",
+    7: "E_VERIFY", 8: "E_NOT_ON_CURVE",
 }
 
 
@@ -107,13 +107,16 @@ class Library:
         return self.lib.pb254_trace_rows(n_inputs, min_rows)
 
 
-    def verify(self, proof_words, inputs, timestamps) -> bool:
-        """pb254_verify: True, or raises Pb254Error(E_VERIFY / ...) naming the failed check."""
+    def verify(self, kind, proof_words, inputs, timestamps, config: "Config | None" = None) -> bool:
+        """pb254_verify(kind, config, ...): True, or raises Pb254Error(E_VERIFY / ...) naming the failed check.
+        `kind` and `config` (None = standard_fast_config) are the verifier's own, never the proof's."""
         w = _u64(proof_words)
         inputs = _u64(inputs)
         timestamps = _u64(timestamps)
-        self.check(self.lib.pb254_verify(_p(w), C.c_size_t(w.size), _p(inputs), _p(timestamps),
-                                         C.c_size_t(inputs.shape[0])))
+        if inputs.ndim != 2 or inputs.shape[1] != self.input_words(kind) or timestamps.size != inputs.shape[0]:
+            raise Pb254Error(6, "inputs must be (n, input_words(kind)) with one timestamp per row")
+        self.check(self.lib.pb254_verify(C.c_int(kind), C.byref(config) if config is not None else None, _p(w),
+                                         C.c_size_t(w.size), _p(inputs), _p(timestamps), C.c_size_t(inputs.shape[0])))
         return True
 
 

@@ -171,6 +171,49 @@ def scalar_mul_gen(kind: int, k: int):
     return _to_affine(F, acc)
 
 
+def fq_sqrt(a: int):
+    """Square root in Fq (p = 3 mod 4), or None."""
+    r = pow(a, (BN254_P + 1) // 4, BN254_P)
+    return r if r * r % BN254_P == a % BN254_P else None
+
+
+def fq2_sqrt(a):
+    """Square root in Fq2 = Fq[u]/(u^2 + 1), or None."""
+    a0, a1 = a
+    if a1 == 0:
+        r = fq_sqrt(a0)
+        if r is not None:
+            return (r, 0)
+        r = fq_sqrt(-a0 % BN254_P)
+        return None if r is None else (0, r)
+    n = fq_sqrt((a0 * a0 + a1 * a1) % BN254_P)
+    if n is None:
+        return None
+    half = pow(2, -1, BN254_P)
+    for cand in ((a0 + n) * half % BN254_P, (a0 - n) * half % BN254_P):
+        x0 = fq_sqrt(cand)
+        if x0 is not None and x0 != 0:
+            x1 = a1 * pow(2 * x0, -1, BN254_P) % BN254_P
+            if _Fq2.mul((x0, x1), (x0, x1)) == (a0 % BN254_P, a1 % BN254_P):
+                return (x0, x1)
+    return None
+
+
+G2_B = _Fq2.mul((3, 0), _Fq2.inv((9, 1)))  # b' = 3 / (9 + u)
+
+
+def g2_point_with_x(x):
+    """A point (x, y) of the G2 curve y^2 = x^3 + 3/(9+u) with the given x (any point of the curve, not necessarily
+    of the prime-order subgroup), or None if x^3 + b' is not a square."""
+    y = fq2_sqrt(_Fq2.add(_Fq2.mul(_Fq2.mul(x, x), x), G2_B))
+    return None if y is None else (x, y)
+
+
+def g1_point_with_x(x):
+    y = fq_sqrt((x * x * x + 3) % BN254_P)
+    return None if y is None else (x, y)
+
+
 def _words(x: int):
     return [(x >> (64 * i)) & MASK64 for i in range(4)]
 

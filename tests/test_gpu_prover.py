@@ -96,10 +96,10 @@ def test_product_verifier_accepts_gpu_proofs(gpu_ctx, kind, k):
     from plonky2_bn254_b200 import ffi
     inp, ts = I.make_inputs(kind, k, I.config_seed(80 + kind))
     w = gpu_ctx.prove(kind, inp, ts).words()
-    assert gpu_ctx.L.verify(w, inp, ts)
+    assert gpu_ctx.L.verify(kind, w, inp, ts)
     w[300] ^= np.uint64(1)
     with pytest.raises(ffi.Pb254Error) as e:
-        gpu_ctx.L.verify(w, inp, ts)
+        gpu_ctx.L.verify(kind, w, inp, ts)
     assert e.value.code == 7
 
 

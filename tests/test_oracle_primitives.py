@@ -110,3 +110,14 @@ def test_commit_golden(oracle, golden):
         _, lde = oracle.lde_batch(v, g["rate_bits"])
         assert hashlib.sha256(lde.tobytes()).hexdigest() == g["lde_sha256"]
         assert oracle.commit(v, g["rate_bits"], g["cap_height"]).tolist() == g["cap"]
+
+
+def test_streamed_commit_equals_one_shot_commit(oracle):
+    """oracle.commit_streamed (8-column chunks, bounded memory; used for the config-4 cap at 2^24 LDE rows) is the
+    same function as oracle.commit."""
+    from util import rand_field
+    rng = np.random.default_rng(5)
+    for cols in (5, 8, 13, 27):
+        v = rand_field(rng, (cols, 128))
+        for rate_bits, cap_height in ((1, 2), (3, 4)):
+            assert (oracle.commit(v, rate_bits, cap_height) == oracle.commit_streamed(v, rate_bits, cap_height)).all()

@@ -12,7 +12,7 @@ for k in (4096, 8192):
         print(k, "FAILED", e, flush=True); continue
     stages = ctx.timings()
     w = pf.words()
-    t = time.time(); ok = ctx.L.verify(w, inp, ts); tv = time.time() - t
+    t = time.time(); ok = ctx.L.verify(0, w, inp, ts); tv = time.time() - t
     print(f"G1 x {k}: rows 2^{int(w[2])}, wall {wall*1e3:.0f} ms (first call, includes the arena allocation), stages {sum(m for _, m in stages):.0f} ms, "
           f"proof {w.size*8/1e6:.2f} MB, verify {ok} in {tv:.1f} s, inputs generated in {tg:.1f} s", flush=True)
     print("   " + ", ".join(f"{n} {m:.1f}" for n, m in stages), flush=True)

@@ -21,6 +21,6 @@ for name, kind, k, rb in cases:
         print(name, "FAILED:", e, flush=True); continue
     w = pf.words()
     tot = sum(ms for _, ms in ctx.timings())
-    t = time.time(); ok = ctx.L.verify(w, inp, ts); tv = time.time() - t
+    t = time.time(); ok = ctx.L.verify(kind, w, inp, ts, config=cfg); tv = time.time() - t
     print(f"{name}: wall {wall*1e3:.1f} ms (stages {tot:.1f} ms), proof {w.size*8/1e6:.2f} MB, verify {ok} in {tv:.2f} s, inputs {tgen:.1f} s", flush=True)
     print("   " + ", ".join(f"{n} {ms:.1f}" for n, ms in ctx.timings()), flush=True)
