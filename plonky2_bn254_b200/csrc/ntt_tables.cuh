@@ -9,8 +9,6 @@ namespace ntt {
 static constexpr int LOG_T = 13;          // two-level power tables: x^e = lo[e & 8191] * hi[e >> 13]
 static constexpr int T = 1 << LOG_T;
 static constexpr int LOG_M = 2 * LOG_T;   // master root has order 2^26
-static constexpr int TC = 8;              // adjacent columns per strided tile (64-byte segments)
-static constexpr int KC_MAX = 10;
 static constexpr int K1_MAX = 11;
 
 struct Tables {
@@ -32,9 +30,13 @@ static inline void host_build_table(u64 base, std::vector<u64>& lo, std::vector<
   for (int i = 1; i < T; i++) hi[i] = gl::mul(hi[i - 1], step);
 }
 
+struct PlanCache;  // per-size NTT plans and their tables (ntt.cuh), created on first use
+
 struct TableSet {
   u64* dev = nullptr;  // 8 * T words
   Tables t;
+  PlanCache* plans = nullptr;
+  void (*plans_free)(PlanCache*) = nullptr;
   void init(pbStream s) {
     std::vector<u64> all(8 * T), lo, hi;
     u64 W = gl::root_of_unity(LOG_M);
@@ -57,6 +59,8 @@ struct TableSet {
     t.ish_hi = dev + 7 * T;
   }
   void destroy() {
+    if (plans && plans_free) plans_free(plans);
+    plans = nullptr;
     if (dev) pb_dev_free(dev);
     dev = nullptr;
   }
