@@ -145,6 +145,46 @@ int pb254_verify(int kind, const pb254_config* cfg, const uint64_t* proof_words,
  * 10-word header {magic, kind, degree_bits, config[7]} (layout in DESIGN.md). */
 size_t pb254_proof_words(const pb254_proof* proof);
 const uint64_t* pb254_proof_data(const pb254_proof* proof);
+/* ---- proof fields (the consumer of the proof, set_stark_proof_target at src/generators/g1/stark_proof.rs:173-178
+ * and src/starks/common/ctl_values.rs:10-26, walks StarkProofWithMetadata field by field) ------------------------
+ * Where every field of StarkProofWithMetadata lives in a serialized proof: offsets and sizes in u64 words from the
+ * start of the blob. An extension element is 2 words, a Merkle cap 4 * 2^cap_height words, a hash 4 words.
+ * Field names are starky's (proof.rs: StarkProof, StarkOpeningSet) and plonky2's (fri/proof.rs: FriProof,
+ * FriQueryRound, FriInitialTreeProof, FriQueryStep). Needs no context and no GPU. */
+#define PB254_MAX_FRI_LAYERS 16
+typedef struct pb254_proof_layout {
+  uint32_t kind, degree_bits;
+  pb254_config config;              /* as stamped into the header */
+  uint32_t trace_width;             /* W */
+  uint32_t aux_width;               /* A: lookup helper columns, lookup Z and CTL Z columns */
+  uint32_t quotient_width;          /* Q = 2 * num_challenges */
+  uint32_t num_ctl_zs;              /* 2 * num_challenges (two cross-table lookups) */
+  uint32_t num_fri_layers;          /* commit-phase reductions */
+  uint32_t fri_arity_bits[PB254_MAX_FRI_LAYERS];
+  uint64_t words;                   /* total length of the blob */
+  uint64_t cap_words;               /* 4 * 2^cap_height */
+  uint64_t init_challenger_state;   /* 12 words  (StarkProofWithMetadata::init_challenger_state) */
+  uint64_t trace_cap, auxiliary_polys_cap, quotient_polys_cap;  /* cap_words each */
+  uint64_t local_values, next_values;                   /* 2 W each   (openings) */
+  uint64_t auxiliary_polys, auxiliary_polys_next;       /* 2 A each */
+  uint64_t ctl_zs_first;                                /* num_ctl_zs base-field words */
+  uint64_t quotient_polys;                              /* 2 Q */
+  uint64_t commit_phase_merkle_caps;                    /* num_fri_layers x cap_words */
+  uint64_t query_round_proofs;                          /* config.num_query_rounds records of query_words */
+  uint64_t query_words;
+  uint64_t final_poly, final_poly_words;                /* 2 words per coefficient */
+  uint64_t pow_witness;                                 /* 1 word */
+  /* inside one query record (offsets from the start of the record): initial_trees_proof = the three oracles'
+   * (leaf values, Merkle siblings bottom-up), then one FriQueryStep (evals, siblings) per layer */
+  uint32_t initial_path_words;      /* 4 * (degree_bits + rate_bits - cap_height) */
+  uint32_t q_trace_leaf, q_trace_path, q_aux_leaf, q_aux_path, q_quotient_leaf, q_quotient_path;
+  uint32_t q_step_evals[PB254_MAX_FRI_LAYERS], q_step_evals_words[PB254_MAX_FRI_LAYERS];
+  uint32_t q_step_path[PB254_MAX_FRI_LAYERS], q_step_path_words[PB254_MAX_FRI_LAYERS];
+} pb254_proof_layout;
+/* Checks the header and the length of a serialized proof and fills the layout. PB254_E_BAD_ARG if the words are
+ * not a proof blob or the length does not match the header. */
+int pb254_proof_parse(const uint64_t* proof_words, size_t n_words, pb254_proof_layout* out);
+
 /* The batch's native outputs, read from the trace instead of being recomputed on the CPU: for instance k the
  * 16-bit limbs (one per word) of s*x + offset (G1: x, y; G2: x.c0, x.c1, y.c0, y.c1) or x^s (Fq). run_once
  * computes exactly these with arkworks before proving (src/generators/g1/stark_proof.rs:143-149) and the MSM

@@ -473,6 +473,13 @@ int pb254_verify(int kind, const pb254_config* cfg_in, const uint64_t* proof_wor
 void pb254_proof_free(pb254_proof* p) { delete p; }
 size_t pb254_proof_results_words(const pb254_proof* p) { return p->results.size(); }
 const uint64_t* pb254_proof_results_data(const pb254_proof* p) { return p->results.data(); }
+int pb254_proof_parse(const uint64_t* proof_words, size_t n_words, pb254_proof_layout* out) {
+  return guarded([&] {
+    if (!proof_words || !out) throw Pb254Error(PB254_E_BAD_ARG, "null argument");
+    proofview::parse(proof_words, n_words, *out);
+  });
+}
+
 size_t pb254_proof_words(const pb254_proof* p) { return p->data.blob.size(); }
 const uint64_t* pb254_proof_data(const pb254_proof* p) { return p->data.blob.data(); }
 // debug artefacts kept when keep_debug != 0: 0 auxiliary values (A x n), 1 quotient chunk coefficients

@@ -15,6 +15,7 @@
 #include "aux.cuh"
 #include "quotient.h"
 #include "fri.cuh"
+#include "proofview.cuh"
 #include <vector>
 
 namespace prover {
@@ -59,16 +60,8 @@ struct Challenger {
   }
 };
 
-static inline std::vector<unsigned> fri_arities(const pb254_config& c, unsigned degree_bits) {
-  std::vector<unsigned> r;
-  while (degree_bits > c.final_poly_bits && degree_bits + c.rate_bits >= c.cap_height + c.arity_bits) {
-    r.push_back(c.arity_bits);
-    degree_bits -= c.arity_bits;
-  }
-  return r;
-}
-
-static const u64 PROOF_MAGIC = 0x31465250343532ULL | ((u64)'B' << 56);
+using proofview::fri_arities;
+static const u64 PROOF_MAGIC = proofview::MAGIC;
 
 struct ProofData {
   std::vector<u64> blob;

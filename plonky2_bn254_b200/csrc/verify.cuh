@@ -451,42 +451,29 @@ static inline void verify_proof(int kind, const pb254_config& cfg, const u64* bl
   const size_t n = (size_t)1 << L, N = n << r, ncap = (size_t)1 << cap_h, capw = ncap * 4;
   if (cap_h > logN) throw VerifyError("cap height");
   const std::vector<unsigned> arities = prover::fri_arities(cfg, (unsigned)L);
-  // ---- layout ------------------------------------------------------------------------------------
-  size_t pos = 10;
-  const u64* state = blob + pos;
-  pos += 12;
-  const u64* caps = blob + pos;
-  pos += 3 * capw;
-  const u64* op_tr = blob + pos;
-  pos += 4 * (size_t)W;
-  const u64* op_ax = blob + pos;
-  pos += 4 * (size_t)A;
-  const u64* zs_first = blob + pos;
-  pos += 2 * (size_t)nch;
-  const u64* op_q = blob + pos;
-  pos += 2 * (size_t)Q;
-  const u64* fri_caps = blob + pos;
-  pos += arities.size() * capw;
-  const size_t nq = cfg.num_query_rounds;
-  const int nsib = 4 * (logN - cap_h);
-  size_t rec = (size_t)W + nsib + A + nsib + Q + nsib;
-  {
-    int ll = logN;
-    for (unsigned ab : arities) {
-      ll -= (int)ab;
-      if (ll < cap_h) throw VerifyError("FRI layer smaller than the cap");
-      rec += ((size_t)2 << ab) + 4 * (size_t)(ll - cap_h);
-    }
+  // ---- layout (proofview.cuh) -----------------------------------------------------------------------
+  pb254_proof_layout lay;
+  try {
+    proofview::parse(blob, words, lay);
+  } catch (const Pb254Error& e) {
+    throw VerifyError(std::string(e.what()));
   }
-  const u64* queries = blob + pos;
-  pos += nq * rec;
-  int log_final = L;
-  for (unsigned ab : arities) log_final -= (int)ab;
-  const size_t keep = (size_t)1 << log_final;  // coefficients of the final polynomial (len >> rate_bits)
-  const u64* final_poly = blob + pos;
-  pos += 2 * keep;
-  if (pos + 1 != words) throw VerifyError("proof length does not match its header");
-  const u64 pow_witness = blob[pos];
+  const u64* state = blob + lay.init_challenger_state;
+  const u64* caps = blob + lay.trace_cap;  // trace, auxiliary, quotient caps are consecutive
+  const u64* op_tr = blob + lay.local_values;     // local | next
+  const u64* op_ax = blob + lay.auxiliary_polys;  // aux | aux_next
+  const u64* zs_first = blob + lay.ctl_zs_first;
+  const u64* op_q = blob + lay.quotient_polys;
+  const u64* fri_caps = blob + lay.commit_phase_merkle_caps;
+  const size_t nq = cfg.num_query_rounds;
+  const int nsib = (int)lay.initial_path_words;
+  const size_t rec = lay.query_words;
+  const u64* queries = blob + lay.query_round_proofs;
+  const size_t keep = lay.final_poly_words / 2;  // coefficients of the final polynomial (len >> rate_bits)
+  int log_final = 0;
+  while (((size_t)1 << log_final) < keep) log_final++;
+  const u64* final_poly = blob + lay.final_poly;
+  const u64 pow_witness = blob[lay.pow_witness];
   for (size_t i = 22; i < words; i++)
     if (blob[i] >= gl::P) throw VerifyError("non-canonical field element");
 

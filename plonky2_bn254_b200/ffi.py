@@ -45,6 +45,21 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+class ProofLayout(C.Structure):
+    """pb254_proof_layout (include/pb254.h): offsets and sizes, in u64 words, of the fields of a serialized proof."""
+    _fields_ = ([("kind", C.c_uint32), ("degree_bits", C.c_uint32), ("config", Config)] +
+                [(n, C.c_uint32) for n in ("trace_width", "aux_width", "quotient_width", "num_ctl_zs", "num_fri_layers")] +
+                [("fri_arity_bits", C.c_uint32 * 16)] +
+                [(n, C.c_uint64) for n in (
+                    "words", "cap_words", "init_challenger_state", "trace_cap", "auxiliary_polys_cap",
+                    "quotient_polys_cap", "local_values", "next_values", "auxiliary_polys", "auxiliary_polys_next",
+                    "ctl_zs_first", "quotient_polys", "commit_phase_merkle_caps", "query_round_proofs", "query_words",
+                    "final_poly", "final_poly_words", "pow_witness")] +
+                [(n, C.c_uint32) for n in ("initial_path_words", "q_trace_leaf", "q_trace_path", "q_aux_leaf",
+                                           "q_aux_path", "q_quotient_leaf", "q_quotient_path")] +
+                [(n, C.c_uint32 * 16) for n in ("q_step_evals", "q_step_evals_words", "q_step_path", "q_step_path_words")])
+
+
 class Library:
     """A loaded libpb254 (product) or, for host-logic tests only, the hostsim build."""
 
@@ -82,6 +97,8 @@ class Library:
         L.pb254_proof_results_data.restype = C.POINTER(C.c_uint64)
         L.pb254_proof_results_data.argtypes = [C.c_void_p]
 
+        L.pb254_proof_parse.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(ProofLayout)]
+
     def check(self, rc):
         if rc != 0:
             raise Pb254Error(rc, self.lib.pb254_last_error().decode())
@@ -118,6 +135,78 @@ class Library:
         self.check(self.lib.pb254_verify(C.c_int(kind), C.byref(config) if config is not None else None, _p(w),
                                          C.c_size_t(w.size), _p(inputs), _p(timestamps), C.c_size_t(inputs.shape[0])))
         return True
+
+
+    def parse_proof(self, proof_words) -> "ProofView":
+        """pb254_proof_parse: the fields of StarkProofWithMetadata as views into the serialized proof."""
+        w = _u64(proof_words)
+        lay = ProofLayout()
+        self.check(self.lib.pb254_proof_parse(_p(w), C.c_size_t(w.size), C.byref(lay)))
+        return ProofView(w, lay)
+
+
+class ProofView:
+    """StarkProofWithMetadata rebuilt from the blob, field names of starky's StarkProof / StarkOpeningSet and
+    plonky2's FriProof (what set_stark_proof_target consumes, src/generators/g1/stark_proof.rs:173-178). Every
+    attribute is a numpy view of the blob: extension elements as (.., 2), hashes as (.., 4)."""
+
+    def __init__(self, words: np.ndarray, lay: "ProofLayout"):
+        self.words, self.layout = words, lay
+        w, l = words, lay
+        cw = int(l.cap_words)
+
+        def sl(off, n):
+            return w[int(off):int(off) + int(n)]
+
+        self.kind, self.degree_bits = int(l.kind), int(l.degree_bits)
+        self.config = l.config
+        self.init_challenger_state = sl(l.init_challenger_state, 12)
+        self.trace_cap = sl(l.trace_cap, cw).reshape(-1, 4)
+        self.auxiliary_polys_cap = sl(l.auxiliary_polys_cap, cw).reshape(-1, 4)
+        self.quotient_polys_cap = sl(l.quotient_polys_cap, cw).reshape(-1, 4)
+        W, A, Q = int(l.trace_width), int(l.aux_width), int(l.quotient_width)
+        self.openings = {
+            "local_values": sl(l.local_values, 2 * W).reshape(-1, 2),
+            "next_values": sl(l.next_values, 2 * W).reshape(-1, 2),
+            "auxiliary_polys": sl(l.auxiliary_polys, 2 * A).reshape(-1, 2),
+            "auxiliary_polys_next": sl(l.auxiliary_polys_next, 2 * A).reshape(-1, 2),
+            "ctl_zs_first": sl(l.ctl_zs_first, l.num_ctl_zs),
+            "quotient_polys": sl(l.quotient_polys, 2 * Q).reshape(-1, 2),
+        }
+        nl = int(l.num_fri_layers)
+        self.commit_phase_merkle_caps = sl(l.commit_phase_merkle_caps, nl * cw).reshape(nl, -1, 4)
+        self.final_poly = sl(l.final_poly, l.final_poly_words).reshape(-1, 2)
+        self.pow_witness = int(w[int(l.pow_witness)])
+        ip = int(l.initial_path_words)
+        self.query_round_proofs = []
+        for q in range(int(l.config.num_query_rounds)):
+            rec = sl(int(l.query_round_proofs) + q * int(l.query_words), l.query_words)
+            initial = [(rec[a:a + n], rec[b:b + ip].reshape(-1, 4)) for a, n, b in
+                       ((l.q_trace_leaf, W, l.q_trace_path), (l.q_aux_leaf, A, l.q_aux_path),
+                        (l.q_quotient_leaf, Q, l.q_quotient_path))]
+            steps = [(rec[l.q_step_evals[i]:l.q_step_evals[i] + l.q_step_evals_words[i]].reshape(-1, 2),
+                      rec[l.q_step_path[i]:l.q_step_path[i] + l.q_step_path_words[i]].reshape(-1, 4)) for i in range(nl)]
+            self.query_round_proofs.append({"initial_trees_proof": initial, "steps": steps})
+
+    def serialize(self) -> np.ndarray:
+        """The blob rebuilt field by field (round trip of parse)."""
+        l = self.layout
+        c = l.config
+        out = [self.words[:1], np.array([l.kind, l.degree_bits, c.rate_bits, c.cap_height, c.num_challenges,
+                                         c.num_query_rounds, c.pow_bits, c.arity_bits, c.final_poly_bits], dtype=np.uint64),
+               self.init_challenger_state, self.trace_cap.ravel(), self.auxiliary_polys_cap.ravel(),
+               self.quotient_polys_cap.ravel()]
+        o = self.openings
+        out += [o[k].ravel() for k in ("local_values", "next_values", "auxiliary_polys", "auxiliary_polys_next",
+                                       "ctl_zs_first", "quotient_polys")]
+        out.append(self.commit_phase_merkle_caps.ravel())
+        for q in self.query_round_proofs:
+            for leaf, path in q["initial_trees_proof"]:
+                out += [leaf, path.ravel()]
+            for ev, path in q["steps"]:
+                out += [ev.ravel(), path.ravel()]
+        out += [self.final_poly.ravel(), np.array([self.pow_witness], dtype=np.uint64)]
+        return np.concatenate(out)
 
 
 _default = None

@@ -14,6 +14,8 @@ pub const PB254_E_CUDA: c_int = 4;
 pub const PB254_E_OOM: c_int = 5;
 pub const PB254_E_BAD_ARG: c_int = 6;
 pub const PB254_E_VERIFY: c_int = 7;
+pub const PB254_E_NOT_ON_CURVE: c_int = 8;
+pub const PB254_MAX_FRI_LAYERS: usize = 16;
 
 /// `StarkConfig` (starky config.rs); `standard_fast_config()` = {1, 4, 2, 84, 16, 4, 5}.
 #[repr(C)]
@@ -26,6 +28,51 @@ pub struct pb254_config {
     pub pow_bits: u32,
     pub arity_bits: u32,
     pub final_poly_bits: u32,
+}
+
+/// `pb254_proof_layout`: where every field of `StarkProofWithMetadata` lives in a serialized proof
+/// (offsets and sizes in u64 words), filled by `pb254_proof_parse`.
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct pb254_proof_layout {
+    pub kind: u32,
+    pub degree_bits: u32,
+    pub config: pb254_config,
+    pub trace_width: u32,
+    pub aux_width: u32,
+    pub quotient_width: u32,
+    pub num_ctl_zs: u32,
+    pub num_fri_layers: u32,
+    pub fri_arity_bits: [u32; PB254_MAX_FRI_LAYERS],
+    pub words: u64,
+    pub cap_words: u64,
+    pub init_challenger_state: u64,
+    pub trace_cap: u64,
+    pub auxiliary_polys_cap: u64,
+    pub quotient_polys_cap: u64,
+    pub local_values: u64,
+    pub next_values: u64,
+    pub auxiliary_polys: u64,
+    pub auxiliary_polys_next: u64,
+    pub ctl_zs_first: u64,
+    pub quotient_polys: u64,
+    pub commit_phase_merkle_caps: u64,
+    pub query_round_proofs: u64,
+    pub query_words: u64,
+    pub final_poly: u64,
+    pub final_poly_words: u64,
+    pub pow_witness: u64,
+    pub initial_path_words: u32,
+    pub q_trace_leaf: u32,
+    pub q_trace_path: u32,
+    pub q_aux_leaf: u32,
+    pub q_aux_path: u32,
+    pub q_quotient_leaf: u32,
+    pub q_quotient_path: u32,
+    pub q_step_evals: [u32; PB254_MAX_FRI_LAYERS],
+    pub q_step_evals_words: [u32; PB254_MAX_FRI_LAYERS],
+    pub q_step_path: [u32; PB254_MAX_FRI_LAYERS],
+    pub q_step_path_words: [u32; PB254_MAX_FRI_LAYERS],
 }
 
 #[repr(C)]
@@ -65,8 +112,9 @@ extern "C" {
     pub fn pb254_prove_trace(ctx: *mut pb254_ctx, kind: c_int, trace_cols: *const u64, n_rows: usize,
                              cfg: *const pb254_config, keep_debug: c_int, out: *mut *mut pb254_proof) -> c_int;
     pub fn pb254_proof_free(proof: *mut pb254_proof);
-    pub fn pb254_verify(proof_words: *const u64, n_words: usize, inputs: *const u64, timestamps: *const u64,
-                        n_inputs: usize) -> c_int;
+    pub fn pb254_verify(kind: c_int, cfg: *const pb254_config, proof_words: *const u64, n_words: usize,
+                        inputs: *const u64, timestamps: *const u64, n_inputs: usize) -> c_int;
+    pub fn pb254_proof_parse(proof_words: *const u64, n_words: usize, out: *mut pb254_proof_layout) -> c_int;
     pub fn pb254_proof_results_words(proof: *const pb254_proof) -> usize;
     pub fn pb254_proof_results_data(proof: *const pb254_proof) -> *const u64;
     pub fn pb254_lde_dev(ctx: *mut pb254_ctx, d_values: *const u64, cols: usize, n: usize, rate_bits: u32,

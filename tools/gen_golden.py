@@ -33,6 +33,7 @@ def main():
         inp, ts = I.make_inputs(kind, k, I.config_seed(cid))
         tr, res = O.generate_trace(kind, inp, ts, want_results=True)
         out["traces"].append({"kind": kind, "instances": k, "config_id": cid, "inputs_sha256": sha(inp),
+                              "inputs": [[int(x) for x in r] for r in inp], "timestamps": [int(x) for x in ts],
                               "trace_sha256": sha(tr), "shape": list(tr.shape),
                               "result_limbs": [[int(x) for x in r] for r in res],
                               "frequency_first8": [int(x) for x in tr[tr.shape[0] - 2, :8]]})
@@ -51,9 +52,21 @@ def main():
         pf, _, _ = O.prove_inputs(kind, inp, ts)
         w = pf.words()
         O.verify(w, inp, ts)
+        # sections that do not depend on the proof-of-work witness (the reference's find_any returns an arbitrary valid
+        # witness, so its query rounds may differ): what rust/pb254/tests/golden.rs compares with the Rust crate's proof
+        from plonky2_bn254_b200 import build, ffi
+        lay = ffi.Library(build.build_hostsim()).parse_proof(w).layout
+        sec = {"init_challenger_state": (lay.init_challenger_state, 12),
+               "caps": (lay.trace_cap, 3 * lay.cap_words),
+               "openings": (lay.local_values, lay.commit_phase_merkle_caps - lay.local_values),
+               "commit_phase_merkle_caps": (lay.commit_phase_merkle_caps, lay.num_fri_layers * lay.cap_words),
+               "final_poly": (lay.final_poly, lay.final_poly_words)}
+        w.astype("<u8").tofile(os.path.join(ROOT, "tests", "golden", "fq3_proof.bin"))
         out["proofs"].append({"kind": kind, "instances": k, "config_id": cid, "words": int(w.size),
                               "proof_sha256": sha(w), "trace_cap_first": [int(x) for x in w[22:26]],
-                              "pow_witness": int(w[-1])})
+                              "pow_witness": int(w[-1]), "blob_file": "fq3_proof.bin",
+                              "inputs": [[int(x) for x in r] for r in inp], "timestamps": [int(x) for x in ts],
+                              "sections_sha256": {k2: sha(w[int(a):int(a) + int(n)]) for k2, (a, n) in sec.items()}})
     path = os.path.join(ROOT, "tests", "golden", "golden.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
