@@ -11,6 +11,7 @@
 // the integer pipe (ceil(W/8) permutations per row), not by HBM.
 #pragma once
 #include "poseidon.cuh"
+#include "poseidon_tc.cuh"
 
 namespace merkle {
 
@@ -115,6 +116,42 @@ __global__ void __launch_bounds__(128, 6) k_leaf_hash(const u64* __restrict__ ld
   out[natural ? j : (size_t)gl::brev32((u32)j, log_n)] = d;
 }
 
+// Same kernel with the MDS layers on the tensor cores (poseidon_tc.cuh): one CTA = 128 rows = the 128 rows of the
+// u8 x u8 -> s32 product. Every thread takes part in every permutation (the CTA-wide barrier and the TMEM loads are
+// collective), rows past the end hash row 0 and drop the result.
+__global__ void __launch_bounds__(poseidon::tc::CTA, poseidon::tc::CTAS_PER_SM)
+    k_leaf_hash_tc(const u64* __restrict__ lde, size_t stride, int W, int log_n, Digest* __restrict__ out, size_t rows,
+                   int natural) {
+  extern __shared__ unsigned char tc_dyn[];
+  __shared__ u64 tc_bar;
+  __shared__ u32 tc_slot[2];
+  poseidon::tc::Ctx ctx;
+  poseidon::tc::setup(ctx, tc_dyn, &tc_bar, tc_slot);
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < rows;
+  const u64* p = lde + (live ? j : 0);
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  const int chunks = (W + 7) / 8;
+#pragma unroll 1
+  for (int c = 0; c < chunks; c++) {
+    const int len = W - 8 * c;
+    const u64* q = p + (size_t)c * 8 * stride;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < len) s[k] = q[(size_t)k * stride];
+    poseidon::tc::permute(s, ctx);
+  }
+  if (live) {
+    Digest d;
+#pragma unroll
+    for (int i = 0; i < 4; i++) d.e[i] = s[i];
+    out[natural ? j : (size_t)gl::brev32((u32)j, log_n)] = d;
+  }
+  poseidon::tc::teardown(ctx);
+}
+
 __global__ void __launch_bounds__(128, 6) k_level(const Digest* __restrict__ child, Digest* __restrict__ parent, size_t n) {
   __shared__ __align__(16) u64 rc2[poseidon::RC2_WORDS];
   stage_rc2(rc2);
@@ -177,7 +214,8 @@ static inline void build_from_lde(const u64* lde, size_t stride, int W, int log_
     pb_launch("leaf copy", k, (size_t)1 << log_n, s, 128);
   } else {
     const size_t n = (size_t)1 << log_n;
-    k_leaf_hash<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(lde, stride, W, log_n, digests, n, 0);
+    k_leaf_hash_tc<<<(unsigned)((n + 127) / 128), poseidon::tc::CTA, poseidon::tc::SMEM_BYTES, s>>>(lde, stride, W, log_n,
+                                                                                                  digests, n, 0);
     g_pb_launches++;
     pb_check_last("leaf hash");
   }
@@ -202,7 +240,8 @@ static inline void hash_rows_natural(const u64* m, size_t stride, int W, size_t 
     LeafHashK k{m, stride, W, 0, out, 1};
     pb_launch("leaf copy (rows)", k, rows, s, 128);
   } else {
-    k_leaf_hash<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(m, stride, W, 0, out, rows, 1);
+    k_leaf_hash_tc<<<(unsigned)((rows + 127) / 128), poseidon::tc::CTA, poseidon::tc::SMEM_BYTES, s>>>(m, stride, W, 0, out,
+                                                                                                     rows, 1);
     g_pb_launches++;
     pb_check_last("leaf hash (rows)");
   }

@@ -32,11 +32,20 @@ namespace tc {
 static constexpr int CTA = 128;                 // threads = states = TMEM lanes per CTA
 static constexpr int A_BYTES = 128 * 128;       // state tile
 static constexpr int B_BYTES = 96 * 128;        // MDS + round-constant tile
-static constexpr int SMEM_BYTES = 47 * 1024;    // A + B + alignment slack; also caps residency at 4 CTAs per SM
-static constexpr u32 TMEM_COLS = 128;           // 96 used; allocations are powers of two
-// instruction descriptor (kind::i8): D = s32 (2 << 4), A = B = u8 (0), both K-major, N = 96 (>> 3 at bit 17),
+#ifndef PB_TC_CTAS
+#define PB_TC_CTAS 5
+#endif
+#ifndef PB_TC_LDMODE
+#define PB_TC_LDMODE 2
+#endif
+// Tensor memory: 512 columns per SM, allocations are powers of two >= 32. The 96 accumulator columns are taken as
+// 64 + 32 (two allocations, the product is issued as an N = 64 and an N = 32 half), so FIVE CTAs fit on an SM instead
+// of four; the shared-memory request keeps a sixth from becoming resident (it would spin in tcgen05.alloc).
+static constexpr int CTAS_PER_SM = PB_TC_CTAS;
+static constexpr int SMEM_BYTES = (CTAS_PER_SM == 5 ? 40 : 47) * 1024;  // A + B + alignment slack; caps residency
+// instruction descriptor (kind::i8): D = s32 (2 << 4), A = B = u8 (0), both K-major, N (>> 3 at bit 17),
 // M = 128 (>> 4 at bit 24)
-static constexpr u32 IDESC = (2u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr u32 idesc(u32 n) { return (2u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
 static __device__ const uint4 B_IMAGE[B_BYTES / 16] = {
 #include "poseidon_constants_tcb.inc"
@@ -53,13 +62,12 @@ struct Ctx {
   unsigned char* row;  // this thread's row of the A tile
   u32 r7;              // row & 7: the swizzle of this row
   u32 bar;             // mbarrier (shared address)
-  u32 tmem;            // TMEM address of this warp's 32 lanes, column 0
-  u32 tmem_base;       // as allocated
+  u32 tmem0, tmem1;    // the two TMEM allocations (64 and 32 columns: lanes 0-7 and 8-11 of the state)
   u64 adesc, bdesc;
   u32 parity;
 };
 
-// Called by all 128 threads. dyn: dynamic shared memory (SMEM_BYTES); bar / slot: 8 + 4 bytes of static shared memory.
+// Called by all 128 threads. dyn: dynamic shared memory (SMEM_BYTES); bar / slot: 8 + 2 x 4 bytes of static shared memory.
 __device__ __forceinline__ void setup(Ctx& c, unsigned char* dyn, u64* bar, u32* slot) {
   const u32 t = threadIdx.x;
   unsigned char* base = dyn + ((1024u - (smem_u32(dyn) & 1023u)) & 1023u);
@@ -77,15 +85,15 @@ __device__ __forceinline__ void setup(Ctx& c, unsigned char* dyn, u64* bar, u32*
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (t < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(TMEM_COLS)
-                 : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(slot + 1)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  c.tmem_base = *reinterpret_cast<volatile u32*>(slot);
-  c.tmem = c.tmem_base + (((t >> 5) * 32u) << 16);
+  c.tmem0 = reinterpret_cast<volatile u32*>(slot)[0];
+  c.tmem1 = reinterpret_cast<volatile u32*>(slot)[1];
   c.adesc = smem_desc(smem_u32(a));
   c.bdesc = smem_desc(smem_u32(b));
   c.parity = 0;
@@ -94,10 +102,13 @@ __device__ __forceinline__ void setup(Ctx& c, unsigned char* dyn, u64* bar, u32*
 __device__ __forceinline__ void teardown(const Ctx& c) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x < 32)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem_base), "r"(TMEM_COLS) : "memory");
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(c.tmem0) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(c.tmem1) : "memory");
+  }
 }
 
+template <u32 N>
 __device__ __forceinline__ void mma_i8(u32 d_tmem, u64 adesc, u64 bdesc, u32 accumulate) {
   asm volatile(
       "{\n\t"
@@ -105,7 +116,7 @@ __device__ __forceinline__ void mma_i8(u32 d_tmem, u64 adesc, u64 bdesc, u32 acc
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "n"(idesc(N)), "r"(accumulate)
       : "memory");
 }
 
@@ -161,7 +172,10 @@ __device__ __forceinline__ void mds_layer(u64 s[12], Ctx& c, int L) {
   if (threadIdx.x == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int k = 0; k < 4; k++) mma_i8(c.tmem_base, c.adesc + 2 * k, c.bdesc + 2 * k, k > 0);  // 32 bytes of K per step
+    for (int k = 0; k < 4; k++) {  // 32 bytes of K per step; B rows 0-63 (lanes 0-7) and 64-95 (lanes 8-11)
+      mma_i8<64>(c.tmem0, c.adesc + 2 * k, c.bdesc + 2 * k, k > 0);
+      mma_i8<32>(c.tmem1, c.adesc + 2 * k, c.bdesc + (64 * 128 >> 4) + 2 * k, k > 0);
+    }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.bar) : "memory");
   }
   {
@@ -180,16 +194,48 @@ __device__ __forceinline__ void mds_layer(u64 s[12], Ctx& c, int L) {
     c.parity ^= 1;
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-  for (int g = 0; g < 3; g++) {
+  {
+    const u32 lane_off = ((threadIdx.x >> 5) * 32u) << 16;  // a warp reads the 32 TMEM lanes of its own states
+    const u32 t0 = c.tmem0 + lane_off, t1 = c.tmem0 + lane_off + 32, t2 = c.tmem1 + lane_off;
+#define PB_TC_FOLD(a, base)                                                                                   \
+  _Pragma("unroll") for (int r = 0; r < 4; r++) {                                                             \
+    const u32* q = a + 8 * r;                                                                                 \
+    s[base + r] = recombine4(q[0] + (q[1] << 8), q[2] + (q[3] << 8), q[4] + (q[5] << 8), q[6] + (q[7] << 8)); \
+  }
+#if PB_TC_LDMODE == 0
     u32 a[32];
-    PB_TMEM_LD32(a, c.tmem + 32 * g);
+    PB_TMEM_LD32(a, t0);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const u32* q = a + 8 * r;
-      s[4 * g + r] = recombine4(q[0] + (q[1] << 8), q[2] + (q[3] << 8), q[4] + (q[5] << 8), q[6] + (q[7] << 8));
-    }
+    PB_TC_FOLD(a, 0)
+    PB_TMEM_LD32(a, t1);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    PB_TC_FOLD(a, 4)
+    PB_TMEM_LD32(a, t2);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    PB_TC_FOLD(a, 8)
+#elif PB_TC_LDMODE == 1
+    u32 a[96];
+    PB_TMEM_LD32((a + 0), t0);
+    PB_TMEM_LD32((a + 32), t1);
+    PB_TMEM_LD32((a + 64), t2);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    PB_TC_FOLD((a + 0), 0)
+    PB_TC_FOLD((a + 32), 4)
+    PB_TC_FOLD((a + 64), 8)
+#else
+    // the next 32 columns are in flight while the previous 32 are folded
+    u32 a[32], b[32];
+    PB_TMEM_LD32(a, t0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    PB_TMEM_LD32(b, t1);
+    PB_TC_FOLD(a, 0)
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    PB_TMEM_LD32(a, t2);
+    PB_TC_FOLD(b, 4)
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    PB_TC_FOLD(a, 8)
+#endif
+#undef PB_TC_FOLD
   }
 }
 

@@ -39,10 +39,15 @@ def _int256(words) -> int:
     return sum(int(w) << (64 * i) for i, w in enumerate(words))
 
 
+def _from_limbs16(limbs) -> int:
+    """A 256-bit value from the 16 little-endian 16-bit limbs of the trace (src/starks/mod.rs:13-20)."""
+    return sum(int(w) << (16 * i) for i, w in enumerate(limbs))
+
+
 def is_square_outputs(results) -> np.ndarray:
     """``legendre.is_equal(one)`` (fq.rs:293-294) for the native results ``x^((p-1)/2)`` of an fq_exp proof
-    (``Proof.results()``, [n, 4] little-endian words)."""
-    return np.array([_int256(r) == 1 for r in np.asarray(results).reshape(-1, 4)], dtype=bool)
+    (``Proof.results()``: 16 limbs of 16 bits per instance, as they stand in the trace)."""
+    return np.array([_from_limbs16(r) == 1 for r in np.asarray(results).reshape(-1, 16)], dtype=bool)
 
 
 # ---- hash_to_fq2 ---------------------------------------------------------------------------------------------
@@ -190,6 +195,14 @@ def _g2_from_words(w):
     return ((_int256(w[0:4]), _int256(w[4:8])), (_int256(w[8:12]), _int256(w[12:16])))
 
 
+def _g2_from_limbs16(l):
+    return ((_from_limbs16(l[0:16]), _from_limbs16(l[16:32])), (_from_limbs16(l[32:48]), _from_limbs16(l[48:64])))
+
+
+def _g2_limbs16(P):
+    return [(c >> (16 * i)) & 0xFFFF for c in (P[0][0], P[0][1], P[1][0], P[1][1]) for i in range(16)]
+
+
 def hash_to_g2_inputs(messages, permute, seed: int):
     """G2ScalarMulInput batch of the cofactor clearings of ``hash_to_g2`` over ``messages`` (hash_to_g2.rs:195-203):
     s = cofactor, x = map_to_curve(hash_to_fq2(message)), offset = a random subgroup point (``set_random_g2``).
@@ -210,6 +223,7 @@ def hash_to_g2_inputs(messages, permute, seed: int):
 
 def hash_to_g2_outputs(results, offsets):
     """``output_offset.add(neg_offset)`` (hash_to_g2.rs:204-208): the hash outputs from the native results
-    ``cofactor * point + offset`` of a G2 proof (``Proof.results()``, [n, 16] words)."""
-    res = np.asarray(results).reshape(-1, 16)
-    return [g2_add(_g2_from_words(r), g2_neg(off)) for r, off in zip(res, offsets)]
+    ``cofactor * point + offset`` of a G2 proof (``Proof.results()``: x.c0, x.c1, y.c0, y.c1 as 16 limbs of 16 bits each
+    per instance)."""
+    res = np.asarray(results).reshape(-1, 64)
+    return [g2_add(_g2_from_limbs16(r), g2_neg(off)) for r, off in zip(res, offsets)]

@@ -69,7 +69,7 @@ def test_is_square_inputs_and_outputs():
     assert inp.shape == (6, 8) and (ts == np.arange(6)).all()
     assert Wk._int256(inp[2, :4]) == (P - 1) // 2 and Wk._int256(inp[3, 4:]) == 3
     sym = [pow(x, (P - 1) // 2, P) for x in xs]
-    res = np.array([I._words(s) for s in sym], dtype=np.uint64)
+    res = np.array([[(s >> (16 * i)) & 0xFFFF for i in range(16)] for s in sym], dtype=np.uint64)
     assert Wk.is_square_outputs(res).tolist() == [s == 1 for s in sym]
 
 
@@ -83,7 +83,9 @@ def test_hash_to_g2_inputs_roundtrip_python(oracle):
     for row, off in zip(inp, offs):
         pt = Wk._g2_from_words(row[4:20])
         assert Wk._g2_from_words(row[20:36]) == off
-        res.append(Wk._g2_words(Wk.g2_add(Wk.g2_mul(Wk.G2_COFACTOR, pt), off)))
+        res.append(Wk._g2_limbs16(Wk.g2_add(Wk.g2_mul(Wk.G2_COFACTOR, pt), off)))
+        # the limb layout of Proof.results() is the oracle's native_result layout
+        assert (oracle.native_result(I.KIND_G2, row) == np.array(res[-1], dtype=np.uint64)).all()
     outs = Wk.hash_to_g2_outputs(np.array(res, dtype=np.uint64), offs)
     for row, o in zip(inp, outs):
         assert o == Wk.g2_mul(Wk.G2_COFACTOR, Wk._g2_from_words(row[4:20]))

@@ -18,12 +18,12 @@ __global__ void __launch_bounds__(128, 6) k_ref(const u64* in, u64* out, size_t 
   for (int i = 0; i < 12; i++) out[i * n + j] = s[i];
 }
 
-__global__ void __launch_bounds__(128, 4) k_tc(const u64* in, u64* out, size_t n, int reps) {
+__global__ void __launch_bounds__(128, poseidon::tc::CTAS_PER_SM) k_tc(const u64* in, u64* out, size_t n, int reps) {
   extern __shared__ unsigned char dyn[];
   __shared__ u64 bar;
-  __shared__ u32 slot;
+  __shared__ u32 slot[2];
   poseidon::tc::Ctx c;
-  poseidon::tc::setup(c, dyn, &bar, &slot);
+  poseidon::tc::setup(c, dyn, &bar, slot);
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < n;
   u64 s[12];
@@ -80,7 +80,7 @@ int main(int argc, char** argv) {
     cudaEventElapsedTime(&ms_tc, e0, e1);
   }
   CK(cudaGetLastError());
-  printf("tcgen05: %.3f ms, %.3f Gperm/s\n", ms_tc, n * (double)reps / ms_tc * 1e-6);
+  printf("tcgen05 (ctas %d, ldmode %d): %.3f ms, %.3f Gperm/s\n", PB_TC_CTAS, PB_TC_LDMODE, ms_tc, n * (double)reps / ms_tc * 1e-6);
   std::vector<u64> r1(12 * n), r2(12 * n);
   CK(cudaMemcpy(r1.data(), d1, 96 * n, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(r2.data(), d2, 96 * n, cudaMemcpyDeviceToHost));
