@@ -106,6 +106,30 @@ int pb254_leaf_hash_rows_dev(pb254_ctx* ctx, const uint64_t* d_matrix, size_t st
 int pb254_merkle_subtree_dev(pb254_ctx* ctx, const uint64_t* d_all_digests, uint32_t log_total, size_t first,
                              uint32_t log_sub, uint32_t log_roots, uint64_t* d_roots_out);
 
+/* ---- ONE proof across the GPUs of a node (BASELINE config 5) ----------------------------------
+ * prove() of src/starks/common/prover.rs:18-72 for a single oversized trace, one process per GPU, every rank calling
+ * pb254_prove_sharded with the same inputs. The transcript is replicated (every rank derives the same challenges from
+ * the same caps), the heavy stages are sharded:
+ *   commitments (trace, auxiliary)  LDE of a column shard -> all_to_all -> leaf hashing of a row block -> all_gather of
+ *                                   the digests -> inner levels
+ *   quotient evaluation             row blocks of the LDE with a next-row halo -> all_gather of the values
+ *   FRI combination                 row blocks -> all_gather
+ *   query openings                  rows from the rank that owns them -> all_gather
+ * and the proof is byte-identical to the single-GPU proof on every rank. The collectives are the CALLER's (its own
+ * NCCL communicator: torch.distributed in plonky2_bn254_b200/dist.py, an NCCL binding in a Rust caller): the library
+ * calls back with device pointers on the context's GPU; the callee must enqueue the collective on the context's
+ * stream (or order it after prior and before later work of that stream) and return 0 on success. */
+typedef struct pb254_comm {
+  uint32_t rank, world; /* world: a power of two, <= 2^cap_height, dividing the LDE height */
+  void* user;
+  /* send: world chunks of bytes_per_peer, chunk q goes to rank q; recv: chunk q came from rank q */
+  int (*all_to_all)(void* user, const void* d_send, void* d_recv, size_t bytes_per_peer);
+  /* recv: world chunks of bytes_per_rank in rank order */
+  int (*all_gather)(void* user, const void* d_send, void* d_recv, size_t bytes_per_rank);
+} pb254_comm;
+int pb254_prove_sharded(pb254_ctx* ctx, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
+                        size_t min_rows, const pb254_config* cfg, const pb254_comm* comm, pb254_proof** out);
+
 /* ---- trace generation (K1 + K2) -------------------------------------------------------------- */
 /* generate_trace(&inputs, min_rows): fills cols_out, column-major pb254_trace_width(kind) x
  * pb254_trace_rows(n_inputs, min_rows), with the bit-exact trace of the reference. min_rows must make

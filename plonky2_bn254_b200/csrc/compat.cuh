@@ -15,6 +15,7 @@
 #include <string>
 #include <atomic>
 #include <mutex>
+#include <algorithm>
 
 typedef uint64_t u64;
 typedef uint32_t u32;
@@ -44,6 +45,10 @@ static inline void pb_h2d(void* d, const void* h, size_t n, pbStream) { memcpy(d
 static inline void pb_d2h(void* h, const void* d, size_t n, pbStream) { memcpy(h, d, n); }
 static inline void pb_d2d(void* d, const void* s, size_t n, pbStream) { memmove(d, s, n); }
 static inline void pb_memset(void* d, int v, size_t n, pbStream) { memset(d, v, n); }
+// `height` rows of `width` bytes, row r at d + r * dpitch / s_ + r * spitch (device to device)
+static inline void pb_copy2d(void* d, size_t dpitch, const void* s_, size_t spitch, size_t width, size_t height, pbStream) {
+  for (size_t r = 0; r < height; r++) memmove((char*)d + r * dpitch, (const char*)s_ + r * spitch, width);
+}
 static inline void pb_sync(pbStream) {}
 static inline void pb_set_device(int) {}
 
@@ -94,6 +99,11 @@ static inline void pb_d2d(void* d, const void* s_, size_t n, pbStream s) {
   PB_CUDA(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s));
 }
 static inline void pb_memset(void* d, int v, size_t n, pbStream s) { PB_CUDA(cudaMemsetAsync(d, v, n, s)); }
+// `height` rows of `width` bytes, row r at d + r * dpitch / s_ + r * spitch (device to device)
+static inline void pb_copy2d(void* d, size_t dpitch, const void* s_, size_t spitch, size_t width, size_t height,
+                             pbStream s) {
+  if (width && height) PB_CUDA(cudaMemcpy2DAsync(d, dpitch, s_, spitch, width, height, cudaMemcpyDeviceToDevice, s));
+}
 static inline void pb_sync(pbStream s) { PB_CUDA(cudaStreamSynchronize(s)); }
 static inline void pb_set_device(int d) { PB_CUDA(cudaSetDevice(d)); }
 

@@ -100,6 +100,11 @@ struct WeightedFinalK {
 struct CombineK {
   const u64 *tr, *ax, *qt;
   size_t N;
+  // Row-block form (prover.cuh, one proof across several GPUs): the matrices hold the rows [i_base, i_base + count) of
+  // the LDE with their own column strides and out[il] (natural order) is the value of row i_base + il.
+  // Whole-domain form: strides = N, i_base = 0, natural_out = 0 (bit-reversed output index).
+  size_t tr_stride, ax_stride, qt_stride, i_base = 0;
+  int natural_out = 0;
   int W, A, Q, nlk, nz;  // nlk = first CTL-Z column inside the auxiliary matrix, nz = 2 * num_challenges
   const E2* apow;        // alpha^c, c < W + A + Q
   E2 O0, O1, O2;         // sum_j alpha^j opening_j per batch
@@ -107,17 +112,18 @@ struct CombineK {
   ntt::Tables t;
   int log_N;
   E2* out;  // bit-reversed order
-  PB_HD void operator()(size_t i) const {
+  PB_HD void operator()(size_t il) const {
+    const size_t i = i_base + il;
     const u64 x = gl::mul(gl::COSET_SHIFT, ntt::tpow(t.fwd_lo, t.fwd_hi, (u64)i << (ntt::LOG_M - log_N)));
     gl::Acc sa, sb, fa, fb;
     for (int c = 0; c < W; c++) {
-      u64 v = tr[(size_t)c * N + i];
+      u64 v = tr[(size_t)c * tr_stride + il];
       E2 a = apow[c];
       sa.mac(a.a, v);
       sb.mac(a.b, v);
     }
     for (int c = 0; c < A; c++) {
-      u64 v = ax[(size_t)c * N + i];
+      u64 v = ax[(size_t)c * ax_stride + il];
       E2 a = apow[W + c];
       sa.mac(a.a, v);
       sb.mac(a.b, v);
@@ -130,7 +136,7 @@ struct CombineK {
     E2 s_ta = gl::e2(sa.reduce(), sb.reduce());
     gl::Acc qa, qb;
     for (int q = 0; q < Q; q++) {
-      u64 v = qt[(size_t)q * N + i];
+      u64 v = qt[(size_t)q * qt_stride + il];
       E2 a = apow[W + A + q];
       qa.mac(a.a, v);
       qb.mac(a.b, v);
@@ -141,8 +147,15 @@ struct CombineK {
     E2 t1 = gl::emul(gl::esub(s_ta, O1), gl::einv(gl::e2(gl::sub(x, zeta_next.a), gl::neg(zeta_next.b))));
     E2 t2 = gl::emul_base(gl::esub(f2, O2), gl::inv(gl::sub(x, 1)));
     E2 r = gl::eadd(gl::emul(gl::eadd(gl::emul(t0, sh1), t1), sh2), t2);
-    out[gl::brev32((u32)i, log_N)] = r;
+    out[natural_out ? il : (size_t)gl::brev32((u32)i, log_N)] = r;
   }
+};
+// natural order -> bit-reversed order (row-block form of the combination, after the all-gather)
+struct BitReverseE2K {
+  const E2* in;
+  E2* out;
+  int log_N;
+  PB_HD void operator()(size_t i) const { out[gl::brev32((u32)i, log_N)] = in[i]; }
 };
 
 // ---- K11 fold ----------------------------------------------------------------------------------
@@ -207,6 +220,9 @@ struct Section {
   int log_n;     // log2(number of leaves)
   const u64* ptr;
   size_t stride;
+  // Row-block form: a type-0 section with rows > 0 holds only the LDE rows [row0, row0 + rows); other rows read as 0
+  // (the owning rank supplies them, prover.cuh adds the ranks' records up). Sections with rows == 0 are whole.
+  size_t row0 = 0, rows = 0;
 };
 static constexpr int MAX_SECTIONS = 32;
 struct GatherK {
@@ -214,6 +230,7 @@ struct GatherK {
   int nsec, rec_words;
   const u64* indices;
   u64* out;
+  int zero_whole = 0;  // row-block form: ranks other than 0 write 0 for the sections every rank holds in full
   PB_HD void operator()(size_t gid) const {
     size_t q = gid / rec_words;
     int w = (int)(gid % rec_words);
@@ -224,7 +241,12 @@ struct GatherK {
     int r = w - s.off;
     size_t idx = (size_t)(indices[q] >> s.shift);
     u64 v;
-    if (s.type == 0) {
+    if (s.type == 0 && s.rows) {
+      const size_t row = gl::brev32((u32)idx, s.log_n);
+      v = (row >= s.row0 && row < s.row0 + s.rows) ? s.ptr[(size_t)r * s.stride + (row - s.row0)] : 0;
+    } else if (zero_whole) {
+      v = 0;
+    } else if (s.type == 0) {
       v = s.ptr[(size_t)r * s.stride + gl::brev32((u32)idx, s.log_n)];
     } else if (s.type == 1) {
       int lv = r >> 2;

@@ -285,7 +285,7 @@ int pb254_generate_trace(pb254_ctx* c, int kind, const uint64_t* inputs, const u
 // src/generators/g1/stark_proof.rs:154 and :163. The trace never leaves the device.
 static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
                              size_t min_rows, const pb254_config* cfg_in, int keep_debug, pb254_proof** out,
-                             bool inputs_on_device) {
+                             bool inputs_on_device, const pb254_comm* comm = nullptr) {
   return guarded([&] {
     need(out != nullptr, "null out pointer");
     need_ctx(c);
@@ -297,7 +297,10 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
     const pb254_config cfg = config_or_default(cfg_in, need_trace_rows(n_rows));
     size_t twords = (size_t)l.width * n_rows;
     size_t tg_bytes = tg::scratch_bytes(kind, n_inputs) + n_inputs * (l.in_words + 1) * 8 + 65536;
-    size_t pv_bytes = prover::workspace_bytes(kind, n_rows, cfg);
+    need(!comm || (comm->world >= 1 && (comm->world & (comm->world - 1)) == 0 && comm->rank < comm->world),
+         "comm: world must be a power of two and rank < world");
+    size_t pv_bytes = comm && comm->world > 1 ? prover::workspace_bytes_sharded(kind, n_rows, cfg, comm->world)
+                                              : prover::workspace_bytes(kind, n_rows, cfg);
     c->arena.reserve(twords * 8 + (tg_bytes > pv_bytes ? tg_bytes : pv_bytes) + 65536);
     c->arena.reset();
     c->times.clear();
@@ -331,7 +334,7 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
     pb254_proof* pf = new pb254_proof();
     pf->results.swap(results);
     try {
-      prover::prove_device(c, kind, d_trace, n_rows, cfg, pf->data, keep_debug != 0);
+      prover::prove_device(c, kind, d_trace, n_rows, cfg, pf->data, keep_debug != 0, comm);
     } catch (...) {
       delete pf;
       throw;
@@ -340,6 +343,14 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
     c->times.resolve();
     *out = pf;
   });
+}
+
+// One proof across the ranks of `comm` (include/pb254.h): every rank generates the whole trace (trace generation is
+// 3 % of a proof) and runs the same transcript; the commitments, the quotient, the FRI combination and the query
+// openings are sharded. world == 1 (or comm == NULL) is pb254_prove.
+int pb254_prove_sharded(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
+                        size_t min_rows, const pb254_config* cfg, const pb254_comm* comm, pb254_proof** out) {
+  return prove_inputs_impl(c, kind, inputs, timestamps, n_inputs, min_rows, cfg, 0, out, false, comm);
 }
 
 int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,

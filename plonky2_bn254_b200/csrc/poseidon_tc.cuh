@@ -35,9 +35,6 @@ static constexpr int B_BYTES = 96 * 128;        // MDS + round-constant tile
 #ifndef PB_TC_CTAS
 #define PB_TC_CTAS 5
 #endif
-#ifndef PB_TC_LDMODE
-#define PB_TC_LDMODE 2
-#endif
 // Tensor memory: 512 columns per SM, allocations are powers of two >= 32. The 96 accumulator columns are taken as
 // 64 + 32 (two allocations, the product is issued as an N = 64 and an N = 32 half), so FIVE CTAs fit on an SM instead
 // of four; the shared-memory request keeps a sixth from becoming resident (it would spin in tcgen05.alloc).
@@ -155,6 +152,15 @@ __device__ __forceinline__ u64 recombine4(u32 acc0, u32 acc1, u32 acc2, u32 acc3
   return ((u64)hi << 32) | lo;
 }
 
+// Measured and dropped (tools/microbench/poseidon_tc_test.cu, 2^20 states x 16 permutations; this form: 1.246 Gperm/s,
+// the dp2a form 1.09): one 128-column allocation and one N = 96 product per K step with four CTAs per SM (1.20); one
+// persistent CTA of 4 or 5 groups of 128 threads on named barriers owning all 512 columns (1.20 / 1.16, top stall
+// `barrier`); one TMEM wait for all 96 columns (1.22); the fold in plain 128-bit integer code (ptxas moves a third
+// of it to the FMA pipe but emits 23 instead of 19 instructions: 1.13); the wrap correction of the multiplication on
+// the FMA pipe (1.23); twelve S-boxes unrolled (1.25, not worth the code); the S-box of a partial round interleaved
+// with the folds of the other eleven lanes (1.24). ncu (profiles/): 18.1 k thread-instructions per permutation against
+// 24.5 k, issue slots 64 % busy, ALU pipe 71 %, FMA pipe 24 %, tensor pipe 20 %.
+
 // s <- MDS s + constants of round L + 1, all 128 threads of the CTA together
 __device__ __forceinline__ void mds_layer(u64 s[12], Ctx& c, int L) {
 #pragma unroll
@@ -202,27 +208,6 @@ __device__ __forceinline__ void mds_layer(u64 s[12], Ctx& c, int L) {
     const u32* q = a + 8 * r;                                                                                 \
     s[base + r] = recombine4(q[0] + (q[1] << 8), q[2] + (q[3] << 8), q[4] + (q[5] << 8), q[6] + (q[7] << 8)); \
   }
-#if PB_TC_LDMODE == 0
-    u32 a[32];
-    PB_TMEM_LD32(a, t0);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    PB_TC_FOLD(a, 0)
-    PB_TMEM_LD32(a, t1);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    PB_TC_FOLD(a, 4)
-    PB_TMEM_LD32(a, t2);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    PB_TC_FOLD(a, 8)
-#elif PB_TC_LDMODE == 1
-    u32 a[96];
-    PB_TMEM_LD32((a + 0), t0);
-    PB_TMEM_LD32((a + 32), t1);
-    PB_TMEM_LD32((a + 64), t2);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    PB_TC_FOLD((a + 0), 0)
-    PB_TC_FOLD((a + 32), 4)
-    PB_TC_FOLD((a + 64), 8)
-#else
     // the next 32 columns are in flight while the previous 32 are folded
     u32 a[32], b[32];
     PB_TMEM_LD32(a, t0);
@@ -234,7 +219,6 @@ __device__ __forceinline__ void mds_layer(u64 s[12], Ctx& c, int L) {
     PB_TC_FOLD(b, 4)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     PB_TC_FOLD(a, 8)
-#endif
 #undef PB_TC_FOLD
   }
 }

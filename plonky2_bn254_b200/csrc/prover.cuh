@@ -95,6 +95,36 @@ static inline size_t workspace_bytes(int kind, size_t n, const pb254_config& cfg
   return words * 8 + (size_t)quot::num_constraints(kind, (int)nch) * nch * 8 + (1u << 22);
 }
 
+// the same when the proof is spread over `world` ranks (prove_device with a communicator): row blocks instead of whole
+// LDEs, plus the column-shard LDE, the exchange buffers and the gathered digests
+static inline size_t workspace_bytes_sharded(int kind, size_t n, const pb254_config& cfg, size_t world) {
+  tg::Layout l = tg::layout_for(kind);
+  size_t nch = cfg.num_challenges, W = l.width, A = aux::num_aux(l, (int)nch), Q = 2 * nch;
+  size_t N = n << cfg.rate_bits, halo = (size_t)1 << cfg.rate_bits, Nloc = N / world;
+  size_t WA = W > A ? W : A, cper = (WA + world - 1) / world, Cpad = cper * world;
+  size_t words = (W + A + 2 * world) * (Nloc + halo) + Q * N    // row blocks, quotient LDE
+                 + cper * n + A * n                             // NTT scratch, aux values
+                 + cper * N + Cpad * (Nloc + halo)                 // column-shard LDE, send buffer
+                 + 4 * (Nloc + N)                               // digests of the own rows, of all rows
+                 + 4 * nch * n * 2 + 2 * nch * n + (nch << 16) + 4 * nch * (n / 256 + 16) + 2 * n
+                 + WA * fri::PARTS * 4 + 6 * (W + A + Q) + 3 * N + 2 * Nloc + 2 * N
+                 + 4 * (3 * 2 * N + 2 * N);
+  return words * 8 + (size_t)quot::num_constraints(kind, (int)nch) * nch * 8 + (1u << 22);
+}
+
+// out[i] = sum over `parts` records of in[p * words + i] (u64 wrap-around; exactly one rank holds a non-zero value)
+struct SumRecordsK {
+  const u64* in;
+  u64* out;
+  size_t words;
+  int parts;
+  PB_HD void operator()(size_t i) const {
+    u64 v = 0;
+    for (int p = 0; p < parts; p++) v += in[(size_t)p * words + i];
+    out[i] = v;
+  }
+};
+
 struct Stage {
   pb254_ctx* c;
   int id;
@@ -105,8 +135,11 @@ struct Stage {
 };
 
 // d_trace: W x n column-major device matrix (trace values on H). Fills out.blob.
+// comm != nullptr with world > 1: ONE proof across the ranks of `comm` (include/pb254.h
+// pb254_prove_sharded); every rank holds the whole trace, runs the same transcript and produces the same proof,
+// the commitments, the quotient evaluation, the FRI combination and the query openings are sharded.
 static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size_t n, const pb254_config& cfg,
-                                ProofData& out, bool keep_debug) {
+                                ProofData& out, bool keep_debug, const pb254_comm* comm = nullptr) {
   validate_config(cfg);
   pbStream s = c->stream;
   Arena& ar = c->arena;
@@ -121,6 +154,64 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   if (cap_h > logN) throw Pb254Error(PB254_E_BAD_ARG, "cap_height too large");
   std::vector<unsigned> arities = fri_arities(cfg, (unsigned)L);
   const size_t WA = W > A ? W : A;
+  const bool sharded = comm && comm->world > 1;
+  const size_t P = sharded ? comm->world : 1, rk = sharded ? comm->rank : 0;
+  const size_t Nloc = N / P, halo = (size_t)1 << r;  // LDE rows per rank; the next trace row is 2^r LDE rows further
+  if (sharded) {
+    if ((P & (P - 1)) || rk >= P || !comm->all_to_all || !comm->all_gather)
+      throw Pb254Error(PB254_E_BAD_ARG, "comm: world must be a power of two, rank < world, callbacks non-null");
+    if (Nloc < 256 || keep_debug) throw Pb254Error(PB254_E_BAD_ARG, "comm: too many ranks for this trace (or keep_debug set)");
+  }
+  auto coll = [&](int rc, const char* what) {
+    if (rc) throw Pb254Error(PB254_E_CUDA, std::string("collective failed: ") + what);
+  };
+  struct RowBlock {
+    const u64* ptr;
+    size_t stride;
+  };
+  // PolynomialBatch::from_values of one matrix across the ranks: LDE of this rank's column shard, one all-to-all into
+  // row blocks (plus the next-row halo), leaf hashing of the own rows, all-gather of the digests, inner levels.
+  // Returns this rank's rows [rk Nloc, (rk + 1) Nloc + halo) of all C columns; dig receives the whole tree.
+  auto commit_sharded = [&](const u64* values, int C, Digest* dig, u64* scratch_, const char* tag) -> RowBlock {
+    const size_t cper = ((size_t)C + P - 1) / P, Cpad = cper * P;
+    const size_t c0 = std::min((size_t)C, rk * cper), c1 = std::min((size_t)C, c0 + cper), nc = c1 - c0;
+    const size_t stride = Nloc + halo;
+    u64* rows = ar.alloc_n<u64>(Cpad * stride);
+    const size_t mark = ar.off;
+    u64* col_lde = ar.alloc_n<u64>(cper * N);
+    const std::string t = tag;
+    {
+      Stage st(c, ("lde " + t).c_str());
+      if (nc) ntt::lde_columns(c->tables, values + c0 * n, n, col_lde, N, scratch_, (int)nc, L, r, ntt::FROM_VALUES_LDE, s);
+    }
+    {
+      // Chunk q of the exchange: rows [q Nloc, (q + 1) Nloc + halo) (mod N) of this rank's columns, so that the
+      // receiver's buffer IS its row block with the next-row halo: [source rank][column][Nloc + halo] = [Cpad][stride].
+      Stage st(c, ("exchange " + t).c_str());
+      u64* send = ar.alloc_n<u64>(P * cper * stride);
+      for (size_t q = 0; q < P; q++) {
+        u64* dst = send + q * cper * stride;
+        if (q + 1 < P) {
+          pb_copy2d(dst, stride * 8, col_lde + q * Nloc, N * 8, stride * 8, cper, s);
+        } else {  // the halo of the last block wraps around to row 0
+          pb_copy2d(dst, stride * 8, col_lde + q * Nloc, N * 8, Nloc * 8, cper, s);
+          pb_copy2d(dst + Nloc, stride * 8, col_lde, N * 8, halo * 8, cper, s);
+        }
+      }
+      coll(comm->all_to_all(comm->user, send, rows, cper * stride * 8), "all_to_all");
+    }
+    {
+      Stage st(c, ("merkle " + t).c_str());
+      Digest* mine = ar.alloc_n<Digest>(Nloc);
+      Digest* all = ar.alloc_n<Digest>(N);
+      merkle::hash_rows_natural(rows, stride, C, Nloc, mine, s);
+      coll(comm->all_gather(comm->user, mine, all, Nloc * sizeof(Digest)), "all_gather (digests)");
+      pb_launch("leaves in tree order", merkle::SubtreeLeavesK{all, dig, 0, logN}, N, s, 128);
+      merkle::build_levels(dig, logN, cap_h, s);
+    }
+    ar.off = mark;  // the temporaries are dead in stream order
+    return RowBlock{rows, stride};
+  };
 
   std::vector<u64>& blob = out.blob;
   blob.clear();
@@ -138,17 +229,23 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   blob.resize(blob.size() + 12);
 
   // ---- trace commitment (common/prover.rs:31-44) ----------------------------------------------
-  u64* scratch = ar.alloc_n<u64>(WA * n);
-  u64* lde_tr = ar.alloc_n<u64>((size_t)W * N);
+  u64* scratch = ar.alloc_n<u64>((sharded ? std::max((WA + P - 1) / P, (size_t)Q) : WA) * n);
   const size_t nd = merkle::tree_digests(logN, cap_h);
   Digest* dig_tr = ar.alloc_n<Digest>(nd);
-  {
-    Stage st(c, "lde trace");
-    ntt::lde_columns(c->tables, d_trace, n, lde_tr, N, scratch, W, L, r, ntt::FROM_VALUES_LDE, s);
-  }
-  {
-    Stage st(c, "merkle trace");
-    merkle::build_from_lde(lde_tr, N, W, logN, cap_h, dig_tr, s);
+  RowBlock rb_tr;  // the rows of the trace LDE this rank holds: all of them, or its block
+  if (sharded) {
+    rb_tr = commit_sharded(d_trace, W, dig_tr, scratch, "trace");
+  } else {
+    u64* lde_tr = ar.alloc_n<u64>((size_t)W * N);
+    {
+      Stage st(c, "lde trace");
+      ntt::lde_columns(c->tables, d_trace, n, lde_tr, N, scratch, W, L, r, ntt::FROM_VALUES_LDE, s);
+    }
+    {
+      Stage st(c, "merkle trace");
+      merkle::build_from_lde(lde_tr, N, W, logN, cap_h, dig_tr, s);
+    }
+    rb_tr = RowBlock{lde_tr, N};
   }
   std::vector<u64> cap(ncap * 4);
   pb_d2h(cap.data(), dig_tr + (nd - ncap), ncap * 32, s);
@@ -174,15 +271,21 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     ar.off = mark;
   }
   ch.compact(&blob[pos_state]);
-  u64* lde_ax = ar.alloc_n<u64>((size_t)A * N);
   Digest* dig_ax = ar.alloc_n<Digest>(nd);
-  {
-    Stage st(c, "lde aux");
-    ntt::lde_columns(c->tables, aux_vals, n, lde_ax, N, scratch, A, L, r, ntt::FROM_VALUES_LDE, s);
-  }
-  {
-    Stage st(c, "merkle aux");
-    merkle::build_from_lde(lde_ax, N, A, logN, cap_h, dig_ax, s);
+  RowBlock rb_ax;
+  if (sharded) {
+    rb_ax = commit_sharded(aux_vals, A, dig_ax, scratch, "aux");
+  } else {
+    u64* lde_ax = ar.alloc_n<u64>((size_t)A * N);
+    {
+      Stage st(c, "lde aux");
+      ntt::lde_columns(c->tables, aux_vals, n, lde_ax, N, scratch, A, L, r, ntt::FROM_VALUES_LDE, s);
+    }
+    {
+      Stage st(c, "merkle aux");
+      merkle::build_from_lde(lde_ax, N, A, logN, cap_h, dig_ax, s);
+    }
+    rb_ax = RowBlock{lde_ax, N};
   }
   pb_d2h(cap.data(), dig_ax + (nd - ncap), ncap * 32, s);
   pb_sync(s);
@@ -229,11 +332,18 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   {
     Stage st(c, "quotient eval");
     quot::Params qp;
-    qp.tr = lde_tr;
-    qp.tr_stride = N;
-    qp.ax = lde_ax;
-    qp.ax_stride = N;
-    qp.out = qvals;
+    qp.tr = rb_tr.ptr;
+    qp.tr_stride = rb_tr.stride;
+    qp.ax = rb_ax.ptr;
+    qp.ax_stride = rb_ax.stride;
+    // sharded: this rank evaluates the points of its own LDE rows into [nch][qloc], gathered below
+    const size_t qloc = qsize / P;
+    u64* q_mine = sharded ? ar.alloc_n<u64>((size_t)nch * qloc) : nullptr;
+    qp.out = sharded ? q_mine : qvals;
+    qp.i_base = rk * qloc;
+    qp.count = qloc;
+    qp.out_stride = sharded ? qloc : qsize;
+    qp.wrap = sharded ? 0 : 1;
     qp.weights = d_w;
     qp.bpow = d_bpow;
     qp.bpow_stride = bpow_stride;
@@ -265,6 +375,13 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
       quot::run_g2(qp, s);
     else
       quot::run_fq(qp, s);
+    if (sharded) {
+      u64* q_all = ar.alloc_n<u64>((size_t)nch * qsize);  // [rank][challenge][qloc]
+      coll(comm->all_gather(comm->user, q_mine, q_all, (size_t)nch * qloc * 8), "all_gather (quotient values)");
+      for (size_t p = 0; p < P; p++)
+        for (int j = 0; j < nch; j++)
+          pb_d2d(qvals + (size_t)j * qsize + p * qloc, q_all + (p * nch + j) * qloc, qloc * 8, s);
+    }
   }
   {
     Stage st(c, "quotient intt");
@@ -303,19 +420,48 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     E2* d_op = ar.alloc_n<E2>(2 * WA);
     const E2 scale = gl::emul_base(gl::esub(zeta_pow_n, gl::e2(1, 0)), gl::inv((u64)n % gl::P));
     pb_launch("bary weights", fri::BaryWeightsK{wz, zeta, c->tables.t, L}, n, s, 128);
-    // The transcript absorbs [local | aux | quotient], [next | aux_next], [ctl_zs_first]; every batch of opened
-    // values is hashed on the host while the GPU evaluates the next one (the observe ORDER is unchanged).
-    E2* d_op2 = ar.alloc_n<E2>(2 * WA);
-    pb_launch("open trace", fri::WeightedPartialK{d_trace, n, n, wz, partial, 1}, (size_t)W * fri::PARTS, s, 256);
-    pb_launch("open trace fin", fri::WeightedFinalK{partial, scale, d_op, d_op + W}, W, s, 64);
-    pb_d2h(op_tr.data(), d_op, (size_t)W * 32, s);
-    pb_sync(s);
-    pb_launch("open aux", fri::WeightedPartialK{aux_vals, n, n, wz, partial, 1}, (size_t)A * fri::PARTS, s, 256);
-    pb_launch("open aux fin", fri::WeightedFinalK{partial, scale, d_op2, d_op2 + A}, A, s, 64);
-    // (host hashing comes before the copy: a device-to-host copy into pageable memory blocks the host)
-    ch.observe_n(op_tr.data(), 2 * (size_t)W);  // local trace values, overlapped with the auxiliary openings
-    pb_d2h(op_ax.data(), d_op2, (size_t)A * 32, s);
-    pb_sync(s);
+    if (sharded) {
+      // every rank evaluates the columns of its own shard; all-gather of the 2 x cper extension values per rank
+      auto open_sharded = [&](const u64* vals, int C, std::vector<u64>& op) {
+        const size_t cper = ((size_t)C + P - 1) / P;
+        const size_t c0 = std::min((size_t)C, rk * cper), c1 = std::min((size_t)C, c0 + cper), nc = c1 - c0;
+        E2* d_mine = ar.alloc_n<E2>(2 * cper);
+        E2* d_all = ar.alloc_n<E2>(P * 2 * cper);
+        pb_memset(d_mine, 0, 2 * cper * sizeof(E2), s);
+        if (nc) {
+          pb_launch("open shard", fri::WeightedPartialK{vals + c0 * n, n, n, wz, partial, 1}, nc * fri::PARTS, s, 256);
+          pb_launch("open shard fin", fri::WeightedFinalK{partial, scale, d_mine, d_mine + cper}, nc, s, 64);
+        }
+        coll(comm->all_gather(comm->user, d_mine, d_all, 2 * cper * sizeof(E2)), "all_gather (openings)");
+        std::vector<u64> h(P * 4 * cper);
+        pb_d2h(h.data(), d_all, h.size() * 8, s);
+        pb_sync(s);
+        for (size_t col = 0; col < (size_t)C; col++) {
+          const size_t q = col / cper, j = col % cper;
+          for (int e = 0; e < 2; e++) {
+            op[2 * col + e] = h[((q * 2 + 0) * cper + j) * 2 + e];                 // at zeta
+            op[2 * ((size_t)C + col) + e] = h[((q * 2 + 1) * cper + j) * 2 + e];   // at g zeta
+          }
+        }
+      };
+      open_sharded(d_trace, W, op_tr);
+      ch.observe_n(op_tr.data(), 2 * (size_t)W);
+      open_sharded(aux_vals, A, op_ax);
+    } else {
+      // The transcript absorbs [local | aux | quotient], [next | aux_next], [ctl_zs_first]; every batch of opened
+      // values is hashed on the host while the GPU evaluates the next one (the observe ORDER is unchanged).
+      E2* d_op2 = ar.alloc_n<E2>(2 * WA);
+      pb_launch("open trace", fri::WeightedPartialK{d_trace, n, n, wz, partial, 1}, (size_t)W * fri::PARTS, s, 256);
+      pb_launch("open trace fin", fri::WeightedFinalK{partial, scale, d_op, d_op + W}, W, s, 64);
+      pb_d2h(op_tr.data(), d_op, (size_t)W * 32, s);
+      pb_sync(s);
+      pb_launch("open aux", fri::WeightedPartialK{aux_vals, n, n, wz, partial, 1}, (size_t)A * fri::PARTS, s, 256);
+      pb_launch("open aux fin", fri::WeightedFinalK{partial, scale, d_op2, d_op2 + A}, A, s, 64);
+      // (host hashing comes before the copy: a device-to-host copy into pageable memory blocks the host)
+      ch.observe_n(op_tr.data(), 2 * (size_t)W);  // local trace values, overlapped with the auxiliary openings
+      pb_d2h(op_ax.data(), d_op2, (size_t)A * 32, s);
+      pb_sync(s);
+    }
     pb_launch("zeta powers", fri::PowTableK{wz, zeta}, n, s, 128);
     pb_launch("open quotient", fri::WeightedPartialK{qcoef, n, n, wz, partial, 0}, (size_t)Q * fri::PARTS, s, 256);
     pb_launch("open quotient fin", fri::WeightedFinalK{partial, gl::e2(1, 0), d_op, nullptr}, Q, s, 64);
@@ -363,9 +509,14 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   {
     Stage st(c, "fri combine");
     fri::CombineK k;
-    k.tr = lde_tr;
-    k.ax = lde_ax;
-    k.qt = lde_q;
+    k.tr = rb_tr.ptr;
+    k.ax = rb_ax.ptr;
+    k.qt = lde_q + rk * Nloc;
+    k.tr_stride = rb_tr.stride;
+    k.ax_stride = rb_ax.stride;
+    k.qt_stride = N;
+    k.i_base = rk * Nloc;
+    k.natural_out = sharded ? 1 : 0;
     k.N = N;
     k.W = W;
     k.A = A;
@@ -383,7 +534,16 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     k.t = c->tables.t;
     k.log_N = logN;
     k.out = V;
-    pb_launch("fri combine", k, N, s, 128);
+    if (sharded) {
+      E2* v_mine = ar.alloc_n<E2>(Nloc);
+      E2* v_nat = ar.alloc_n<E2>(N);
+      k.out = v_mine;
+      pb_launch("fri combine", k, Nloc, s, 128);
+      coll(comm->all_gather(comm->user, v_mine, v_nat, Nloc * sizeof(E2)), "all_gather (combined polynomial)");
+      pb_launch("bit reverse", fri::BitReverseE2K{v_nat, V, logN}, N, s, 128);
+    } else {
+      pb_launch("fri combine", k, N, s, 128);
+    }
     pb_sync(s);  // apow (host vector) must outlive the H2D copy
   }
   struct Layer {
@@ -497,16 +657,20 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     for (auto& x : idx) x = ch.challenge() % (u64)N;
     fri::GatherK gk;
     int ns = 0, off = 0;
-    auto add = [&](int type, int words, int shift, int log_n, const void* ptr, size_t stride) {
+    auto add = [&](int type, int words, int shift, int log_n, const void* ptr, size_t stride, bool block = false) {
       if (ns >= fri::MAX_SECTIONS) throw Pb254Error(PB254_E_BAD_ARG, "too many proof sections");
       gk.sec[ns] = fri::Section{type, off, words, shift, log_n, (const u64*)ptr, stride};
+      if (block) {  // only the rows of this rank's block are here
+        gk.sec[ns].row0 = rk * Nloc;
+        gk.sec[ns].rows = Nloc;
+      }
       off += words;
       ns++;
     };
     const int nsib = 4 * (logN - cap_h);
-    add(0, W, 0, logN, lde_tr, N);
+    add(0, W, 0, logN, rb_tr.ptr, rb_tr.stride, sharded);
     add(1, nsib, 0, logN, dig_tr, 0);
-    add(0, A, 0, logN, lde_ax, N);
+    add(0, A, 0, logN, rb_ax.ptr, rb_ax.stride, sharded);
     add(1, nsib, 0, logN, dig_ax, 0);
     add(0, Q, 0, logN, lde_q, N);
     add(1, nsib, 0, logN, dig_q, 0);
@@ -523,7 +687,13 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     pb_h2d(d_idx, idx.data(), nq * 8, s);
     gk.indices = d_idx;
     gk.out = d_out;
+    gk.zero_whole = sharded && rk != 0;
     pb_launch("query gather", gk, nq * (size_t)off, s, 128);
+    if (sharded) {  // every word of a record is non-zero on at most one rank: gather the records and add them up
+      u64* d_all = ar.alloc_n<u64>(P * nq * (size_t)off);
+      coll(comm->all_gather(comm->user, d_out, d_all, nq * (size_t)off * 8), "all_gather (query records)");
+      pb_launch("merge query records", SumRecordsK{d_all, d_out, nq * (size_t)off, (int)P}, nq * (size_t)off, s, 128);
+    }
     size_t pos = blob.size();
     blob.resize(pos + nq * (size_t)off);
     pb_d2h(&blob[pos], d_out, nq * (size_t)off * 8, s);

@@ -16,6 +16,12 @@ struct Params {
   int bpow_stride;
   size_t size;        // quotient domain size = 2 n
   int log_size;
+  // Row-block form (one proof across several GPUs, prover.cuh): this call evaluates the `count` points
+  // [i_base, i_base + count); tr / ax hold the LDE rows of exactly these points followed by the 2 * step rows of the
+  // next-row halo (no wrap-around inside the block), out is [nch][out_stride] with point i_base at index 0.
+  // Whole-domain form: i_base = 0, count = size, out_stride = size, wrap = 1.
+  size_t i_base, count, out_stride;
+  int wrap;
   size_t step;        // LDE index of quotient point i is i * step  (2^(rate_bits - 1))
   ntt::Tables t;
   u64 g;              // root of unity of order n

@@ -10,10 +10,10 @@ int num_constraints(int kind, int nch) {
 }
 
 void run_g1(const Params& p, pbStream s) {
-  pb_launch_lb<64, 16>("quotient g1 pass 0", QuotientK<0, 0>{p}, p.size, s);
-  pb_launch("quotient g1 pass 1", QuotientK<0, 1>{p}, p.size, s, 64);
-  pb_launch_lb<64, 16>("quotient g1 pass 2", QuotientK<0, 2>{p}, p.size, s);  // 64 registers: no scratch arrays in this pass
-  pb_launch_lb<64, 16>("quotient g1 pass 3", QuotientK<0, 3>{p}, p.size, s);
+  pb_launch_lb<64, 16>("quotient g1 pass 0", QuotientK<0, 0>{p}, p.count, s);
+  pb_launch("quotient g1 pass 1", QuotientK<0, 1>{p}, p.count, s, 64);
+  pb_launch_lb<64, 16>("quotient g1 pass 2", QuotientK<0, 2>{p}, p.count, s);  // 64 registers: no scratch arrays in this pass
+  pb_launch_lb<64, 16>("quotient g1 pass 3", QuotientK<0, 3>{p}, p.count, s);
 }
 
 }  // namespace quot

@@ -369,9 +369,11 @@ struct QuotientK {
     for (int i = 0; i < n; i++) E.term(q_sub(TL(ix, colx + i), TL(iy, coly + i)));
   }
 
-  PB_HD void operator()(size_t i) const {
-    const size_t i_next = (i + 2) & (p.size - 1);  // next_step = 2^quotient_degree_bits = 2
-    const size_t i0 = i * p.step, i1 = i_next * p.step;
+  PB_HD void operator()(size_t il) const {
+    // il: index inside this call's block (the storage index), i: index in the quotient domain
+    const size_t i = p.i_base + il;
+    const size_t i_next = p.wrap ? ((il + 2) & (p.size - 1)) : il + 2;  // next_step = 2^quotient_degree_bits = 2
+    const size_t i0 = il * p.step, i1 = i_next * p.step;
     const int nch = p.ch.nch;
     const int L = Y::L;
     Emit E(p.weights, nch);
@@ -544,7 +546,7 @@ struct QuotientK {
     for (int j = 0; j < aux::MAXCH; j++)
       if (j < nch) {
         u64 v = E.total[j];
-        u64* o = p.out + (size_t)j * p.size + i;
+        u64* o = p.out + (size_t)j * p.out_stride + il;
         if (PASS > 0) v = gl::add(*o, v);
         if (PASS == NPASS - 1) v = gl::mul(v, p.zh_inv[i & 1]);
         *o = v;

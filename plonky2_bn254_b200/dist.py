@@ -149,3 +149,60 @@ def dist_commit(ctx, dist, shard, total_cols: int, rate_bits: int, cap_height: i
     if timings is not None:
         timings.update(t)
     return cap
+
+
+# ---- ONE proof across the GPUs of a node (pb254_prove_sharded, include/pb254.h) -------------------------------------
+class TorchCollectives:
+    """The two collectives pb254_prove_sharded calls back for, on raw pointers, through torch.distributed.
+
+    CUDA (NCCL): the pointers are device pointers on the context's GPU; they are wrapped without a copy through
+    ``__cuda_array_interface__`` and the collectives are issued with the context's stream current, so they are ordered
+    with the prover's kernels like any other work of that stream. CPU (gloo, the hostsim build of the tests): host
+    pointers wrapped with ``torch.frombuffer``."""
+
+    def __init__(self, dist, device, torch_stream=None):
+        import torch
+        self.torch, self.dist, self.device, self.stream = torch, dist, torch.device(device), torch_stream
+        self.bytes_all_to_all = 0
+        self.bytes_all_gather = 0
+        self.calls = 0
+
+    def _view(self, ptr: int, nbytes: int):
+        torch = self.torch
+        if self.device.type == "cuda":
+            class _Buf:
+                pass
+            b = _Buf()
+            b.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            return torch.as_tensor(b, device=self.device)
+        import ctypes
+        return torch.frombuffer((ctypes.c_char * nbytes).from_address(ptr), dtype=torch.uint8)
+
+    def _on_stream(self):
+        import contextlib
+        if self.device.type == "cuda" and self.stream is not None:
+            return self.torch.cuda.stream(self.stream)
+        return contextlib.nullcontext()
+
+    def all_to_all(self, send: int, recv: int, bytes_per_peer: int):
+        world = self.dist.get_world_size()
+        with self._on_stream():
+            self.dist.all_to_all_single(self._view(recv, bytes_per_peer * world), self._view(send, bytes_per_peer * world))
+        self.bytes_all_to_all += bytes_per_peer * (world - 1)
+        self.calls += 1
+
+    def all_gather(self, send: int, recv: int, bytes_per_rank: int):
+        world = self.dist.get_world_size()
+        with self._on_stream():
+            self.dist.all_gather_into_tensor(self._view(recv, bytes_per_rank * world), self._view(send, bytes_per_rank))
+        self.bytes_all_gather += bytes_per_rank * (world - 1)
+        self.calls += 1
+
+
+def prove_sharded(ctx, dist, kind: int, inputs, timestamps, device, torch_stream=None, config=None, min_rows=1 << 16):
+    """One proof of (inputs, timestamps) across all ranks of `dist`; every rank gets the same proof, byte-identical to
+    ctx.prove on one GPU. Returns (Proof, TorchCollectives) - the latter carries the exchanged byte counts."""
+    coll = TorchCollectives(dist, device, torch_stream)
+    pf = ctx.prove_sharded(kind, inputs, timestamps, dist.get_rank(), dist.get_world_size(), coll.all_to_all,
+                           coll.all_gather, min_rows=min_rows, config=config)
+    return pf, coll

@@ -45,6 +45,15 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+_COLL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class Comm(C.Structure):
+    """pb254_comm (include/pb254.h): the caller's collectives for ONE proof across the GPUs of a node."""
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("user", C.c_void_p),
+                ("all_to_all", _COLL_FN), ("all_gather", _COLL_FN)]
+
+
 class ProofLayout(C.Structure):
     """pb254_proof_layout (include/pb254.h): offsets and sizes, in u64 words, of the fields of a serialized proof."""
     _fields_ = ([("kind", C.c_uint32), ("degree_bits", C.c_uint32), ("config", Config)] +
@@ -314,6 +323,35 @@ class Context:
                                             C.c_size_t(inputs.shape[0]), C.c_size_t(min_rows),
                                             C.byref(config) if config is not None else None, C.c_int(int(keep_debug)),
                                             C.byref(h)))
+        return Proof(self.L, h)
+
+    def prove_sharded(self, kind, inputs, timestamps, rank: int, world: int, all_to_all, all_gather,
+                      min_rows=1 << 16, config: Config | None = None):
+        """pb254_prove_sharded: one proof across `world` ranks, every rank calling with the same inputs.
+        all_to_all(send_ptr, recv_ptr, bytes_per_peer) / all_gather(send_ptr, recv_ptr, bytes_per_rank) get raw pointers
+        on this context's device and must run on (or be ordered with) the context's stream; see dist.TorchCollectives."""
+        inputs = _u64(inputs)
+        timestamps = _u64(timestamps)
+        assert inputs.ndim == 2 and inputs.shape[1] == self.L.input_words(kind)
+        errors = []
+
+        def wrap(fn):
+            def cb(_user, send, recv, nbytes):
+                try:
+                    fn(int(send), int(recv), int(nbytes))
+                    return 0
+                except Exception as e:  # an exception must not cross the C frames
+                    errors.append(e)
+                    return 1
+            return _COLL_FN(cb)
+        comm = Comm(rank, world, None, wrap(all_to_all), wrap(all_gather))
+        h = C.c_void_p()
+        rc = self.L.lib.pb254_prove_sharded(self._h, C.c_int(kind), _p(inputs), _p(timestamps),
+                                            C.c_size_t(inputs.shape[0]), C.c_size_t(min_rows),
+                                            C.byref(config) if config is not None else None, C.byref(comm), C.byref(h))
+        if errors:
+            raise errors[0]
+        self.L.check(rc)
         return Proof(self.L, h)
 
     def prove_dev(self, kind, d_inputs_ptr: int, d_timestamps_ptr: int, n_inputs: int, min_rows=1 << 16,

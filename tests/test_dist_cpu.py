@@ -117,3 +117,55 @@ def test_dist_commit_matches_single_commit(oracle, world):
     want = oracle.commit(full, 1, 4).tolist()
     for _, cap in res:
         assert cap == want
+
+
+def _sharded_worker(rank, world, port, kind, k, rate_bits, q):
+    sys.path.insert(0, ROOT)
+    import hashlib
+    import torch.distributed as dist
+    from plonky2_bn254_b200 import build, dist as D, ffi, inputs as I
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, 8 // world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = ffi.Context(0, library=ffi.Library(build.HOSTSIM_LIB))
+    inp, ts = I.make_inputs(kind, k, I.config_seed(70 + kind))
+    cfg = None
+    if rate_bits != 1:
+        cfg = ctx.L.standard_fast_config()
+        cfg.rate_bits, cfg.num_query_rounds = rate_bits, 28
+    pf, coll = D.prove_sharded(ctx, dist, kind, inp, ts, "cpu", config=cfg)
+    w = pf.words()
+    stages = [name for name, _ in ctx.timings()]
+    dist.barrier()
+    q.put((rank, hashlib.sha256(w.tobytes()).hexdigest(), int(w.size), coll.calls, coll.bytes_all_to_all, stages))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,kind,k,rate_bits", [(2, 2, 3, 1), (4, 2, 2, 2)])
+def test_sharded_proof_is_the_single_rank_proof(hostsim_ctx, world, kind, k, rate_bits):
+    """pb254_prove_sharded (one proof across `world` ranks: column-sharded LDE, all-to-all, row-block leaf hashing,
+    row-block quotient with the next-row halo, row-block FRI combination, owner-supplied query rows) gives, on every
+    rank, the bytes of the single-rank proof. gloo + the hostsim build; the GPU tier repeats it over NCCL."""
+    from plonky2_bn254_b200 import inputs as I
+    port = _free_port()
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    procs = [ctxmp.Process(target=_sharded_worker, args=(r, world, port, kind, k, rate_bits, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=900) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    import hashlib
+    inp, ts = I.make_inputs(kind, k, I.config_seed(70 + kind))
+    cfg = None
+    if rate_bits != 1:
+        cfg = hostsim_ctx.L.standard_fast_config()
+        cfg.rate_bits, cfg.num_query_rounds = rate_bits, 28
+    want = hostsim_ctx.prove(kind, inp, ts, config=cfg).words()
+    for rank, sha, size, calls, a2a, stages in res:
+        assert size == want.size and sha == hashlib.sha256(want.tobytes()).hexdigest(), f"rank {rank}"
+        assert calls == 2 * 3 + 3 and a2a > 0          # per matrix: all-to-all, digests, openings; quotient, FRI, queries
+        assert "exchange trace" in stages and "exchange aux" in stages
