@@ -403,6 +403,48 @@ def run_ours(args, rank, world, local_rank):
                           "stage_ms": {a: round(b / args.other_steps, 3) for a, b in st.items()}}
             del d_in, d_ts
 
+    # ---- BASELINE.json config 5: ONE oversized trace proved across all N ranks --------
+    oversized = None
+    if dist is not None and not args.no_oversized:
+        import hashlib
+        from plonky2_bn254_b200 import dist as D
+        for inst in (args.oversized_instances, args.oversized_instances // 2):
+            try:
+                o_inp, o_ts = I.make_inputs(KIND_G1, inst, I.config_seed(5))
+                pf, coll = D.prove_sharded(ctx, dist, KIND_G1, o_inp, o_ts, f"cuda:{local_rank}", torch_stream=stream)
+                pf.close()
+                best, o_stage = None, None
+                for _ in range(args.other_steps):
+                    barrier()
+                    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0.record(stream)
+                    pf, coll = D.prove_sharded(ctx, dist, KIND_G1, o_inp, o_ts, f"cuda:{local_rank}", torch_stream=stream)
+                    s1.record(stream)
+                    barrier()
+                    ms = max_over_ranks(s0.elapsed_time(s1))
+                    if best is None or ms < best:
+                        best, o_stage = ms, ctx.timings()
+                    sha = hashlib.sha256(pf.words().tobytes()).hexdigest()
+                    pf.close()
+                shas = [None] * world
+                dist.all_gather_object(shas, sha)
+                ex = sum(v for k, v in o_stage if k.startswith("exchange"))
+                oversized = {
+                    "workload": f"ONE G1 proof of {inst} scalar-muls ({lib.trace_rows(inst, 1 << 16)} rows x 781 columns) "
+                                f"across {world} GPUs: column-sharded LDE, NCCL all-to-all into row blocks, row-block "
+                                f"hashing / quotient / FRI combination, replicated transcript (pb254_prove_sharded)",
+                    "instances": inst, "trace_rows": lib.trace_rows(inst, 1 << 16), "n_gpus": world,
+                    "ms_per_proof": best, "proofs_per_s": 1e3 / best, "scalar_muls_per_s": inst * 1e3 / best,
+                    "steps": args.other_steps, "warmup": 1, "identical_on_all_ranks": len(set(shas)) == 1,
+                    "all_to_all_bytes_sent_per_rank": coll.bytes_all_to_all,
+                    "all_gather_bytes_received_per_rank": coll.bytes_all_gather, "collective_calls": coll.calls,
+                    "exchange_ms": ex,
+                    "all_to_all_gb_s_per_rank": coll.bytes_all_to_all / (ex * 1e-3) / 1e9 if ex > 0 else None,
+                    "stage_ms": {k: round(v, 3) for k, v in o_stage}}
+                break
+            except ffi.Pb254Error as e:  # the same on every rank (sizes are identical): try half the trace
+                oversized = {"error": str(e), "instances": inst}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -471,6 +513,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if other:
         line["other_configs"] = other
+    if oversized:
+        line["oversized_trace"] = oversized
     if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
         line["cpu_baseline"] = cpu_baseline(args.instances, args.cpu_sample_instances)
     emit(line)
@@ -514,6 +558,9 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the secondary measurements of BASELINE configs 3 (G2 x 1024) and 4 (fq_exp x 4096, blow-up 8)")
     ap.add_argument("--other-steps", type=int, default=2)
+    ap.add_argument("--no-oversized", action="store_true",
+                    help="N > 1: skip the one-proof-across-all-GPUs measurement (BASELINE config 5)")
+    ap.add_argument("--oversized-instances", type=int, default=8192, help="8192 G1 scalar-muls = 2^22 rows (config 5)")
     ap.add_argument("--no-full-check", action="store_true",
                     help="reference arm: skip the one full-workload proof timed before the steps")
     args = ap.parse_args()

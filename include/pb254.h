@@ -148,6 +148,16 @@ int pb254_prove(pb254_ctx* ctx, int kind, const uint64_t* inputs, const uint64_t
  * (same wire format); the batched-pipeline form, where a producer kernel wrote the work items. */
 int pb254_prove_dev(pb254_ctx* ctx, int kind, const uint64_t* d_inputs, const uint64_t* d_timestamps,
                     size_t n_inputs, size_t min_rows, const pb254_config* cfg, int keep_debug, pb254_proof** out);
+/* A stream of independent proofs through several contexts of the SAME GPU (one stream and one workspace each), the
+ * software pipeline of a witness generator that has many batches to prove (the circuit builder registers one
+ * G1/G2/FqStarkProofGenerator per 128-1024 operations, src/generators/g1/stark_proof.rs:136): batch b is proved by
+ * pb254_prove on ctxs[b % n_ctx], the contexts run on their own host threads, so the host-side transcript, the small
+ * kernels and the tail waves of one proof overlap the big kernels of the next. inputs / timestamps: n_batches
+ * consecutive batches of n_inputs instances each (wire format as above). proofs_out: n_batches handles, in batch
+ * order; identical to what pb254_prove returns for each batch. On failure nothing is returned and the first
+ * error is reported. */
+int pb254_prove_many(pb254_ctx* const* ctxs, size_t n_ctx, int kind, const uint64_t* inputs, const uint64_t* timestamps,
+                     size_t n_inputs, size_t n_batches, size_t min_rows, const pb254_config* cfg, pb254_proof** proofs_out);
 /* prove(stark, config, trace, ctls, public_inputs = []) on a host trace, column-major
  * pb254_trace_width(kind) x n_rows (src/starks/common/prover.rs:18-30). */
 int pb254_prove_trace(pb254_ctx* ctx, int kind, const uint64_t* trace_cols, size_t n_rows, const pb254_config* cfg,

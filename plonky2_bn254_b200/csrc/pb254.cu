@@ -7,6 +7,7 @@
 std::atomic<unsigned long long> g_pb_launches{0};
 #include "context.cuh"
 #include "ntt.cuh"
+#include <thread>
 #include "merkle.cuh"
 #include "tracegen.h"
 #include "prover.cuh"
@@ -356,6 +357,44 @@ int pb254_prove_sharded(pb254_ctx* c, int kind, const uint64_t* inputs, const ui
 int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
                 size_t min_rows, const pb254_config* cfg, int keep_debug, pb254_proof** out) {
   return prove_inputs_impl(c, kind, inputs, timestamps, n_inputs, min_rows, cfg, keep_debug, out, false);
+}
+
+int pb254_prove_many(pb254_ctx* const* ctxs, size_t n_ctx, int kind, const uint64_t* inputs, const uint64_t* timestamps,
+                     size_t n_inputs, size_t n_batches, size_t min_rows, const pb254_config* cfg, pb254_proof** proofs_out) {
+  int rc = guarded([&] {
+    need(ctxs && n_ctx > 0 && n_ctx <= 16 && proofs_out, "null contexts / outputs or more than 16 contexts");
+    need_kind(kind);
+    need(inputs && timestamps && n_inputs > 0, "null or empty input");
+    for (size_t t = 0; t < n_ctx; t++) {
+      need_ctx(ctxs[t]);
+      for (size_t u = 0; u < t; u++) need(ctxs[u] != ctxs[t], "the same context twice");
+    }
+  });
+  if (rc) return rc;
+  const size_t in_words = (size_t)shape_for(kind).in_words;
+  for (size_t b = 0; b < n_batches; b++) proofs_out[b] = nullptr;
+  std::vector<int> codes(n_ctx, 0);
+  std::vector<std::string> messages(n_ctx);
+  std::vector<std::thread> workers;
+  for (size_t t = 0; t < n_ctx; t++)
+    workers.emplace_back([&, t] {
+      for (size_t b = t; b < n_batches && !codes[t]; b += n_ctx) {
+        codes[t] = pb254_prove(ctxs[t], kind, inputs + b * n_inputs * in_words, timestamps + b * n_inputs, n_inputs,
+                               min_rows, cfg, 0, &proofs_out[b]);
+        if (codes[t]) messages[t] = pb254_last_error();  // thread-local in this worker
+      }
+    });
+  for (auto& w : workers) w.join();
+  for (size_t t = 0; t < n_ctx; t++)
+    if (codes[t]) {
+      for (size_t b = 0; b < n_batches; b++) {
+        if (proofs_out[b]) pb254_proof_free(proofs_out[b]);
+        proofs_out[b] = nullptr;
+      }
+      g_last_error = messages[t];
+      return codes[t];
+    }
+  return PB254_OK;
 }
 
 // Same with `inputs` / `timestamps` already resident in device memory of the context's GPU.

@@ -221,6 +221,22 @@ class ProofView:
 _default = None
 
 
+def prove_many(contexts, kind, batches, min_rows=1 << 16, config: "Config | None" = None):
+    """pb254_prove_many: `batches` = list of (inputs, timestamps) of equal size, proved round-robin on `contexts` (all on
+    one GPU) by the library's own host threads; returns the proofs in batch order."""
+    L = contexts[0].L
+    inp = np.ascontiguousarray(np.stack([_u64(b[0]) for b in batches]))
+    ts = np.ascontiguousarray(np.stack([_u64(b[1]) for b in batches]))
+    nb, n_inputs = inp.shape[0], inp.shape[1]
+    assert inp.shape[2] == L.input_words(kind) and ts.shape == (nb, n_inputs)
+    handles = (C.c_void_p * nb)()
+    ctxs = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    L.check(L.lib.pb254_prove_many(ctxs, C.c_size_t(len(contexts)), C.c_int(kind), _p(inp), _p(ts), C.c_size_t(n_inputs),
+                                   C.c_size_t(nb), C.c_size_t(min_rows),
+                                   C.byref(config) if config is not None else None, handles))
+    return [Proof(L, C.c_void_p(h)) for h in handles]
+
+
 def default_library() -> Library:
     global _default
     if _default is None:

@@ -125,3 +125,23 @@ def test_second_device_in_the_same_process(gpu_ctx):
     b = ctx1.prove(I.KIND_FQ, inp, ts).words()
     ctx1.close()
     assert (a == b).all()
+
+
+def test_prove_many(gpu_ctx):
+    """pb254_prove_many: proofs of a stream of batches through two contexts on one GPU == pb254_prove per batch; a bad
+    batch fails the whole call with the reference's error code and returns no handles."""
+    from plonky2_bn254_b200 import ffi
+    batches = [I.make_inputs(I.KIND_G1, 4, I.config_seed(120 + b)) for b in range(5)]
+    ctx2 = ffi.Context(0, library=gpu_ctx.L)
+    many = ffi.prove_many([gpu_ctx, ctx2], I.KIND_G1, batches)
+    assert len(many) == 5
+    for b, pf in enumerate(many):
+        want = gpu_ctx.prove(I.KIND_G1, *batches[b]).words()
+        got = pf.words()
+        assert got.size == want.size and (got == want).all(), f"batch {b}"
+    bad = [(b[0].copy(), b[1]) for b in batches]
+    bad[3][0][0, 4:8] = np.uint64(0xFFFFFFFFFFFFFFFF)   # x.x >= p
+    with pytest.raises(ffi.Pb254Error) as e:
+        ffi.prove_many([gpu_ctx, ctx2], I.KIND_G1, bad)
+    assert e.value.code == 3
+    ctx2.close()

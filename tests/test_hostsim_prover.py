@@ -2,6 +2,7 @@
 build, tests/hostsim/), against the oracle: transcript, proof assembly and every per-thread kernel body
 are the same code the GPU runs. The GPU parity tests proper are the `-m gpu` tests."""
 import numpy as np
+import pytest
 
 from plonky2_bn254_b200 import inputs as I
 
@@ -40,3 +41,19 @@ def test_hostsim_commit_matches_oracle(hostsim_ctx, oracle):
     assert (hostsim_ctx.lde_batch(v, 1) == lde).all()
     assert (hostsim_ctx.lde_batch(coeffs, 1, from_coeffs=True) == lde).all()
 
+
+
+def test_prove_many_equals_prove(hostsim_ctx, fq_case):
+    """pb254_prove_many (independent proofs round-robin over several contexts, one host thread each) returns, in batch
+    order, exactly the proofs pb254_prove gives for each batch (batch 0: the session's oracle proof, byte-identical by
+    parity; batch 1: proved again on one context). The failure path is in tests/test_gpu_prover.py."""
+    from plonky2_bn254_b200 import ffi
+    batches = [(fq_case["inputs"], fq_case["timestamps"]), I.make_inputs(I.KIND_FQ, 3, I.config_seed(121))]
+    ctx2 = ffi.Context(0, library=hostsim_ctx.L)
+    many = ffi.prove_many([hostsim_ctx, ctx2], I.KIND_FQ, batches)
+    ctx2.close()
+    assert len(many) == 2
+    want = [fq_case["words"], hostsim_ctx.prove(I.KIND_FQ, *batches[1]).words()]
+    for b, pf in enumerate(many):
+        got = pf.words()
+        assert got.size == want[b].size and (got == want[b]).all(), f"batch {b}"
