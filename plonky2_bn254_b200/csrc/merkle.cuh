@@ -185,19 +185,23 @@ static inline size_t level_offset(int log_n, int lvl) {
   return off;
 }
 
+// parent[i] = two_to_one(child[2 i], child[2 i + 1]) for i < n
+static inline void launch_level(const Digest* child, Digest* parent, size_t n, pbStream s) {
+#if PB_HOSTSIM
+  LevelK k{child, parent};
+  pb_launch("merkle level", k, n, s, 128);
+#else
+  k_level<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(child, parent, n);
+  g_pb_launches++;
+  pb_check_last("merkle level");
+#endif
+}
 static inline void build_levels(Digest* digests, int log_n, int cap_height, pbStream s) {
   if (cap_height > log_n) throw Pb254Error(6, "merkle: cap_height > log2(leaves)");
   size_t off = 0;
   for (int l = 0; l < log_n - cap_height; l++) {
     size_t m = (size_t)1 << (log_n - l);
-#if PB_HOSTSIM
-    LevelK k{digests + off, digests + off + m};
-    pb_launch("merkle level", k, m / 2, s, 128);
-#else
-    k_level<<<(unsigned)((m / 2 + 127) / 128), 128, 0, s>>>(digests + off, digests + off + m, m / 2);
-    g_pb_launches++;
-    pb_check_last("merkle level");
-#endif
+    launch_level(digests + off, digests + off + m, m / 2, s);
     off += m;
   }
 }

@@ -169,6 +169,25 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     const u64* ptr;
     size_t stride;
   };
+  // Inner levels of a tree whose leaf level is complete on every rank: rank q hashes the nodes [q m / P, (q + 1) m / P)
+  // of a level (a contiguous node range at every level is one subtree) and the level is all-gathered, instead of
+  // every rank hashing all of it; the top levels (fewer than 256 nodes per rank) are computed by everyone.
+  // part: scratch for N / (2 P) digests.
+  auto levels_sharded = [&](Digest* dig, Digest* part) {
+    size_t off = 0;
+    for (int lv = 0; lv < logN - cap_h; lv++) {
+      const size_t m = (size_t)1 << (logN - lv), half = m / 2, per = half / P;
+      Digest* child = dig + off;
+      Digest* parent = dig + off + m;
+      if (per >= 256) {
+        merkle::launch_level(child + 2 * rk * per, part, per, s);
+        coll(comm->all_gather(comm->user, part, parent, per * sizeof(Digest)), "all_gather (tree level)");
+      } else {
+        merkle::launch_level(child, parent, half, s);
+      }
+      off += m;
+    }
+  };
   // PolynomialBatch::from_values of one matrix across the ranks: LDE of this rank's column shard, one all-to-all into
   // row blocks (plus the next-row halo), leaf hashing of the own rows, all-gather of the digests, inner levels.
   // Returns this rank's rows [rk Nloc, (rk + 1) Nloc + halo) of all C columns; dig receives the whole tree.
@@ -207,7 +226,7 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
       merkle::hash_rows_natural(rows, stride, C, Nloc, mine, s);
       coll(comm->all_gather(comm->user, mine, all, Nloc * sizeof(Digest)), "all_gather (digests)");
       pb_launch("leaves in tree order", merkle::SubtreeLeavesK{all, dig, 0, logN}, N, s, 128);
-      merkle::build_levels(dig, logN, cap_h, s);
+      levels_sharded(dig, mine);
     }
     ar.off = mark;  // the temporaries are dead in stream order
     return RowBlock{rows, stride};
@@ -393,7 +412,14 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   {
     Stage st(c, "lde+merkle quotient");
     ntt::lde_columns(c->tables, qcoef, n, lde_q, N, scratch, Q, L, r, ntt::FROM_COEFFS_LDE, s);
-    merkle::build_from_lde(lde_q, N, Q, logN, cap_h, dig_q, s);
+    if (sharded) {  // leaves everywhere (Q <= 4 columns are copied, not hashed), inner levels shared out
+      merkle::build_from_lde(lde_q, N, Q, logN, logN, dig_q, s);
+      size_t mk = ar.off;
+      levels_sharded(dig_q, ar.alloc_n<Digest>(Nloc));
+      ar.off = mk;
+    } else {
+      merkle::build_from_lde(lde_q, N, Q, logN, cap_h, dig_q, s);
+    }
   }
   int herr = 0;
   pb_d2h(&herr, d_err, sizeof(int), s);
