@@ -14,6 +14,7 @@
 // inverses come from a 65536-entry table per challenge instead of one field inversion per cell.
 // Bound: HBM (reads the 450 / 900 / 128 range-checked columns once, writes H columns per challenge).
 #pragma once
+#include <functional>
 #include "context.cuh"
 #include "tracegen.h"
 
@@ -100,6 +101,7 @@ struct SumsScanK {  // exclusive scan of the chunk sums of one column (forward o
   u64* sums;
   size_t nchunks;
   int reverse;
+  u64* totals;  // null, or [ncol]: the sum of the whole column (row-block form)
   PB_HD void operator()(size_t col) const {
     u64* p = sums + col * nchunks;
     u64 run = 0;
@@ -109,6 +111,29 @@ struct SumsScanK {  // exclusive scan of the chunk sums of one column (forward o
       p[ck] = run;
       run = gl::add(run, v);
     }
+    if (totals) totals[col] = run;
+  }
+};
+// Row-block form (one proof across several GPUs): the matrix is the row block [rank n, (rank + 1) n) of the whole one;
+// the running sums continue across ranks, so every chunk prefix gets the totals of the ranks before (forward) or
+// after (reverse) this one. gather(send, recv, bytes) is the caller's all-gather.
+struct BlockScan {
+  int world, rank;
+  std::function<void(const void*, void*, size_t)> gather;
+  u64* totals;      // [max columns of one scan]
+  u64* all_totals;  // [world][max columns]
+};
+struct CarryK {
+  u64* sums;
+  size_t nchunks;
+  const u64* all_totals;
+  int ncol, world, rank, reverse;
+  PB_HD void operator()(size_t gid) const {
+    const size_t col = gid / nchunks;
+    u64 carry = 0;
+    for (int p = 0; p < world; p++)
+      if (reverse ? p > rank : p < rank) carry = gl::add(carry, all_totals[(size_t)p * ncol + col]);
+    sums[gid] = gl::add(sums[gid], carry);
   }
 };
 // forward exclusive:  out[i] = sum_{t < i} in[t];   reverse inclusive: out[i] = sum_{t >= i} in[t]
@@ -138,11 +163,16 @@ struct ChunkScanK {
   }
 };
 static inline void scan_columns(const u64* in, u64* sums, u64* out, size_t n, int ncol, int reverse, int out_col0,
-                                int out_col_stride, pbStream s) {
+                                int out_col_stride, pbStream s, const BlockScan* bs = nullptr) {
   if (n % SCAN_CHUNK) throw Pb254Error(6, "scan: n must be a multiple of 256");
   size_t nchunks = n / SCAN_CHUNK;
   pb_launch("scan chunk sums", ChunkSumK{in, sums, n, nchunks}, (size_t)ncol * nchunks, s, 64);
-  pb_launch("scan sums", SumsScanK{sums, nchunks, reverse}, (size_t)ncol, s, 32);
+  pb_launch("scan sums", SumsScanK{sums, nchunks, reverse, bs ? bs->totals : nullptr}, (size_t)ncol, s, 32);
+  if (bs) {
+    bs->gather(bs->totals, bs->all_totals, (size_t)ncol * 8);
+    pb_launch("scan carry", CarryK{sums, nchunks, bs->all_totals, ncol, bs->world, bs->rank, reverse},
+              (size_t)ncol * nchunks, s, 64);
+  }
   pb_launch("scan chunks", ChunkScanK{in, sums, out, n, nchunks, reverse, out_col0, out_col_stride},
             (size_t)ncol * nchunks, s, 64);
 }
@@ -232,19 +262,24 @@ static inline HostCtl host_ctl(const tg::Layout& l) {
 static inline int num_helpers(const tg::Layout& l) { return (l.rc_hi - l.rc_lo + 1) / 2; }
 static inline int num_aux(const tg::Layout& l, int nch) { return (num_helpers(l) + 1) * nch + 2 * nch; }
 
-// Builds the A x n auxiliary matrix on the device.
+// Builds the A x n auxiliary matrix on the device. With `bs`: d_trace / d_aux are the row blocks (n rows each, stride n)
+// of this rank, the running sums continue across the ranks (BlockScan).
 static inline void build(Arena& ar, const tg::Layout& l, const u64* d_trace, size_t n, const Challenges& ch,
-                         u64* d_aux, pbStream s) {
+                         u64* d_aux, pbStream s, BlockScan* bs = nullptr) {
   const int nch = ch.nch, nh = num_helpers(l);
   u64* invt = ar.alloc_n<u64>((size_t)nch << 16);
   u64* xs = ar.alloc_n<u64>((size_t)2 * nch * n);  // reused for the CTL terms
   u64* sums = ar.alloc_n<u64>((size_t)2 * nch * (n / SCAN_CHUNK) + 16);
+  if (bs) {
+    bs->totals = ar.alloc_n<u64>((size_t)2 * nch);
+    bs->all_totals = ar.alloc_n<u64>((size_t)bs->world * 2 * nch);
+  }
   pb_launch("lookup inverse table", InvTableK{invt, ch}, (size_t)nch << 16, s, 128);
   pb_launch("lookup helpers",
             HelpersK{d_trace, d_aux, xs, invt, n, l.rc_lo, l.rc_hi - l.rc_lo, nh, l.freq, l.range_counter, nch}, n, s,
             128);
   // Z_j into column j * (nh + 1) + nh
-  scan_columns(xs, sums, d_aux, n, nch, 0, nh, nh + 1, s);
+  scan_columns(xs, sums, d_aux, n, nch, 0, nh, nh + 1, s, bs);
   HostCtl hc = host_ctl(l);
   int* d_tc = ar.alloc_n<int>(hc.term_col.size());
   u64* d_tk = ar.alloc_n<u64>(hc.term_coef.size());
@@ -261,7 +296,7 @@ static inline void build(Arena& ar, const tg::Layout& l, const u64* d_trace, siz
   d.filter_col[0] = hc.filter_col[0];
   d.filter_col[1] = hc.filter_col[1];
   pb_launch("ctl terms", CtlTermsK{d_trace, xs, d, ch, n}, n, s, 128);
-  scan_columns(xs, sums, d_aux, n, 2 * nch, 1, (nh + 1) * nch, 1, s);
+  scan_columns(xs, sums, d_aux, n, 2 * nch, 1, (nh + 1) * nch, 1, s, bs);
 }
 
 }  // namespace aux

@@ -346,12 +346,85 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
   });
 }
 
-// One proof across the ranks of `comm` (include/pb254.h): every rank generates the whole trace (trace generation is
-// 3 % of a proof) and runs the same transcript; the commitments, the quotient, the FRI combination and the query
-// openings are sharded. world == 1 (or comm == NULL) is pb254_prove.
+// One proof across the ranks of `comm` (include/pb254.h). When the trace splits into per-rank row blocks of whole
+// instances that each hold the 2^16-row range-check table or none of it (n / world a multiple of 512 and >= 65536 -
+// every BASELINE size does), every rank generates only ITS instances: the row block [rank n / P, (rank + 1) n / P) of
+// the trace; the range-check histogram is added up across the ranks and lands in rank 0's frequency column. Otherwise
+// (small traces) every rank generates the whole trace. world == 1 (or comm == NULL) is pb254_prove.
 int pb254_prove_sharded(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,
-                        size_t min_rows, const pb254_config* cfg, const pb254_comm* comm, pb254_proof** out) {
-  return prove_inputs_impl(c, kind, inputs, timestamps, n_inputs, min_rows, cfg, 0, out, false, comm);
+                        size_t min_rows, const pb254_config* cfg_in, const pb254_comm* comm, pb254_proof** out) {
+  if (!comm || comm->world <= 1)
+    return prove_inputs_impl(c, kind, inputs, timestamps, n_inputs, min_rows, cfg_in, 0, out, false, comm);
+  {
+    const size_t n_rows = pb254_trace_rows(n_inputs, min_rows), P = comm->world;
+    const bool pow2 = P && (P & (P - 1)) == 0;
+    if (!pow2 || n_rows % P || (n_rows / P) % tg::PERIOD || n_rows / P < 65536)
+      return prove_inputs_impl(c, kind, inputs, timestamps, n_inputs, min_rows, cfg_in, 0, out, false, comm);
+  }
+  return guarded([&] {
+    need(out != nullptr, "null out pointer");
+    need_ctx(c);
+    need_kind(kind);
+    need(inputs && timestamps && n_inputs > 0, "null or empty input");
+    need(comm->rank < comm->world && comm->all_to_all && comm->all_gather, "comm: rank < world, callbacks non-null");
+    pb_set_device(c->device);
+    const tg::Layout l = tg::layout_for(kind);
+    const size_t n_rows = pb254_trace_rows(n_inputs, min_rows), P = comm->world, rk = comm->rank, nloc = n_rows / P;
+    const pb254_config cfg = config_or_default(cfg_in, need_trace_rows(n_rows));
+    const size_t per = nloc / tg::PERIOD;  // instances per rank
+    const size_t i0 = std::min(n_inputs, rk * per), i1 = std::min(n_inputs, (rk + 1) * per), kloc = i1 - i0;
+    const size_t Wpad = ((size_t)l.width + P - 1) / P * P;
+    const size_t twords = Wpad * nloc;
+    size_t tg_bytes = tg::scratch_bytes(kind, kloc ? kloc : 1) + (kloc + 1) * (l.in_words + 1) * 8 + (P + 1) * 65536 * 8 + 65536;
+    size_t pv_bytes = prover::workspace_bytes_sharded(kind, n_rows, cfg, P);
+    c->arena.reserve(twords * 8 + (tg_bytes > pv_bytes ? tg_bytes : pv_bytes) + 65536);
+    c->arena.reset();
+    c->times.clear();
+    u64* d_rows = c->arena.alloc_n<u64>(twords);
+    size_t mark = c->arena.off;
+    {
+      prover::Stage st(c, "tracegen");
+      u64* d_in = c->arena.alloc_n<u64>(kloc * l.in_words + 1);
+      u64* d_ts = c->arena.alloc_n<u64>(kloc + 1);
+      if (kloc) {
+        pb_h2d(d_in, inputs + i0 * l.in_words, kloc * l.in_words * 8, c->stream);
+        pb_h2d(d_ts, timestamps + i0, kloc * 8, c->stream);
+      }
+      int* d_err = c->arena.alloc_n<int>(1);
+      pb_memset(d_err, 0, sizeof(int), c->stream);
+      tg::generate(c->arena, kind, d_in, d_ts, kloc, nloc, d_rows, d_err, c->stream, rk * nloc);
+      // range-check frequencies: every block counted its own cells into the first 2^16 rows of its frequency column;
+      // the table rows are rows 0 .. 65535 of the whole trace, i.e. of rank 0's block
+      u64* freq = d_rows + (size_t)l.freq * nloc;
+      u64* all = c->arena.alloc_n<u64>(P * 65536);
+      if (comm->all_gather(comm->user, freq, all, 65536 * 8)) throw Pb254Error(PB254_E_CUDA, "collective failed: all_gather");
+      if (rk == 0)
+        pb_launch("sum histograms", prover::SumRecordsK{all, freq, 65536, (int)P}, 65536, c->stream, 128);
+      else
+        pb_memset(freq, 0, 65536 * 8, c->stream);
+      // an input error on one rank must fail the call on every rank (the others would wait in the next collective)
+      u64* e_mine = c->arena.alloc_n<u64>(1);
+      u64* e_all = c->arena.alloc_n<u64>(P);
+      pb_memset(e_mine, 0, 8, c->stream);
+      pb_d2d(e_mine, d_err, sizeof(int), c->stream);
+      if (comm->all_gather(comm->user, e_mine, e_all, 8)) throw Pb254Error(PB254_E_CUDA, "collective failed: all_gather");
+      std::vector<u64> herr(P);
+      pb_d2h(herr.data(), e_all, P * 8, c->stream);
+      pb_sync(c->stream);
+      for (size_t p = 0; p < P; p++) throw_trace_error((int)(herr[p] & 0xffffffffu));
+    }
+    c->arena.off = mark;
+    pb254_proof* pf = new pb254_proof();  // no native results in this mode: they are spread over the ranks
+    try {
+      prover::prove_device(c, kind, d_rows, n_rows, cfg, pf->data, false, comm, true);
+    } catch (...) {
+      delete pf;
+      throw;
+    }
+    pb_sync(c->stream);
+    c->times.resolve();
+    *out = pf;
+  });
 }
 
 int pb254_prove(pb254_ctx* c, int kind, const uint64_t* inputs, const uint64_t* timestamps, size_t n_inputs,

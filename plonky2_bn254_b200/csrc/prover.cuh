@@ -138,8 +138,13 @@ struct Stage {
 // comm != nullptr with world > 1: ONE proof across the ranks of `comm` (include/pb254.h
 // pb254_prove_sharded); every rank holds the whole trace, runs the same transcript and produces the same proof,
 // the commitments, the quotient evaluation, the FRI combination and the query openings are sharded.
+// trace_is_block (sharded only): d_trace is not the whole trace but this rank's row block [rank n / P, (rank + 1) n / P)
+// of it, column-major [ceil(W / P) P columns][n / P] (instance-sharded trace generation, pb254.cu); the column shards
+// the LDE and the openings need are then produced by one more all-to-all of VALUES, and the auxiliary columns are
+// built per row block with the running sums carried across the ranks.
 static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size_t n, const pb254_config& cfg,
-                                ProofData& out, bool keep_debug, const pb254_comm* comm = nullptr) {
+                                ProofData& out, bool keep_debug, const pb254_comm* comm = nullptr,
+                                bool trace_is_block = false) {
   validate_config(cfg);
   pbStream s = c->stream;
   Arena& ar = c->arena;
@@ -169,6 +174,21 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     const u64* ptr;
     size_t stride;
   };
+  const size_t nloc = n / P;  // trace rows per rank
+  auto first_col = [&](int C) { return std::min((size_t)C, rk * (((size_t)C + P - 1) / P)); };
+  // Row blocks of VALUES [ceil(C / P) P][nloc] -> this rank's column shard [ceil(C / P)][n]: chunk q of the all-to-all
+  // is the contiguous slab of rank q's columns, the received slabs are laid side by side along the rows.
+  auto to_column_shard = [&](const u64* rows, int C, const char* tag) -> const u64* {
+    const size_t cper = ((size_t)C + P - 1) / P;
+    u64* shard = ar.alloc_n<u64>(cper * n);
+    const size_t mark = ar.off;
+    Stage st(c, (std::string("values exchange ") + tag).c_str());
+    u64* recv = ar.alloc_n<u64>(cper * n);
+    coll(comm->all_to_all(comm->user, rows, recv, cper * nloc * 8), "all_to_all (values)");
+    for (size_t p = 0; p < P; p++) pb_copy2d(shard + p * nloc, n * 8, recv + p * cper * nloc, nloc * 8, nloc * 8, cper, s);
+    ar.off = mark;
+    return shard;
+  };
   // Inner levels of a tree whose leaf level is complete on every rank: rank q hashes the nodes [q m / P, (q + 1) m / P)
   // of a level (a contiguous node range at every level is one subtree) and the level is all-gathered, instead of
   // every rank hashing all of it; the top levels (fewer than 256 nodes per rank) are computed by everyone.
@@ -191,7 +211,8 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   // PolynomialBatch::from_values of one matrix across the ranks: LDE of this rank's column shard, one all-to-all into
   // row blocks (plus the next-row halo), leaf hashing of the own rows, all-gather of the digests, inner levels.
   // Returns this rank's rows [rk Nloc, (rk + 1) Nloc + halo) of all C columns; dig receives the whole tree.
-  auto commit_sharded = [&](const u64* values, int C, Digest* dig, u64* scratch_, const char* tag) -> RowBlock {
+  // shard: the values of this rank's columns [c0, c1), [nc][n].
+  auto commit_sharded = [&](const u64* shard, int C, Digest* dig, u64* scratch_, const char* tag) -> RowBlock {
     const size_t cper = ((size_t)C + P - 1) / P, Cpad = cper * P;
     const size_t c0 = std::min((size_t)C, rk * cper), c1 = std::min((size_t)C, c0 + cper), nc = c1 - c0;
     const size_t stride = Nloc + halo;
@@ -201,7 +222,7 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     const std::string t = tag;
     {
       Stage st(c, ("lde " + t).c_str());
-      if (nc) ntt::lde_columns(c->tables, values + c0 * n, n, col_lde, N, scratch_, (int)nc, L, r, ntt::FROM_VALUES_LDE, s);
+      if (nc) ntt::lde_columns(c->tables, shard, n, col_lde, N, scratch_, (int)nc, L, r, ntt::FROM_VALUES_LDE, s);
     }
     {
       // Chunk q of the exchange: rows [q Nloc, (q + 1) Nloc + halo) (mod N) of this rank's columns, so that the
@@ -252,8 +273,11 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
   const size_t nd = merkle::tree_digests(logN, cap_h);
   Digest* dig_tr = ar.alloc_n<Digest>(nd);
   RowBlock rb_tr;  // the rows of the trace LDE this rank holds: all of them, or its block
+  if (trace_is_block && !sharded) throw Pb254Error(PB254_E_BAD_ARG, "a row-block trace needs a communicator");
+  const u64* tr_shard = nullptr;  // sharded: the trace values of this rank's columns
   if (sharded) {
-    rb_tr = commit_sharded(d_trace, W, dig_tr, scratch, "trace");
+    tr_shard = trace_is_block ? to_column_shard(d_trace, W, "trace") : d_trace + first_col(W) * n;
+    rb_tr = commit_sharded(tr_shard, W, dig_tr, scratch, "trace");
   } else {
     u64* lde_tr = ar.alloc_n<u64>((size_t)W * N);
     {
@@ -281,19 +305,31 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     chal.beta[j] = ch.challenge();
     chal.gamma[j] = ch.challenge();
   }
-  u64* aux_vals = ar.alloc_n<u64>((size_t)A * n);
+  // whole matrix, or (row-block trace) this rank's row block [ceil(A / P) P][nloc]
+  const size_t Apad = ((size_t)A + P - 1) / P * P;
+  u64* aux_vals = ar.alloc_n<u64>(trace_is_block ? Apad * nloc : (size_t)A * n);
   {
     Stage st(c, "aux columns");
     size_t mark = ar.off;
-    aux::build(ar, l, d_trace, n, chal, aux_vals, s);
+    if (trace_is_block) {
+      aux::BlockScan bs;
+      bs.world = (int)P;
+      bs.rank = (int)rk;
+      bs.gather = [&](const void* a, void* b, size_t bytes) { coll(comm->all_gather(comm->user, a, b, bytes), "all_gather (scan)"); };
+      aux::build(ar, l, d_trace, nloc, chal, aux_vals, s, &bs);
+    } else {
+      aux::build(ar, l, d_trace, n, chal, aux_vals, s);
+    }
     pb_sync(s);
     ar.off = mark;
   }
   ch.compact(&blob[pos_state]);
   Digest* dig_ax = ar.alloc_n<Digest>(nd);
   RowBlock rb_ax;
+  const u64* ax_shard = nullptr;
   if (sharded) {
-    rb_ax = commit_sharded(aux_vals, A, dig_ax, scratch, "aux");
+    ax_shard = trace_is_block ? to_column_shard(aux_vals, A, "aux") : aux_vals + first_col(A) * n;
+    rb_ax = commit_sharded(ax_shard, A, dig_ax, scratch, "aux");
   } else {
     u64* lde_ax = ar.alloc_n<u64>((size_t)A * N);
     {
@@ -448,14 +484,14 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     pb_launch("bary weights", fri::BaryWeightsK{wz, zeta, c->tables.t, L}, n, s, 128);
     if (sharded) {
       // every rank evaluates the columns of its own shard; all-gather of the 2 x cper extension values per rank
-      auto open_sharded = [&](const u64* vals, int C, std::vector<u64>& op) {
+      auto open_sharded = [&](const u64* shard, int C, std::vector<u64>& op) {
         const size_t cper = ((size_t)C + P - 1) / P;
         const size_t c0 = std::min((size_t)C, rk * cper), c1 = std::min((size_t)C, c0 + cper), nc = c1 - c0;
         E2* d_mine = ar.alloc_n<E2>(2 * cper);
         E2* d_all = ar.alloc_n<E2>(P * 2 * cper);
         pb_memset(d_mine, 0, 2 * cper * sizeof(E2), s);
         if (nc) {
-          pb_launch("open shard", fri::WeightedPartialK{vals + c0 * n, n, n, wz, partial, 1}, nc * fri::PARTS, s, 256);
+          pb_launch("open shard", fri::WeightedPartialK{shard, n, n, wz, partial, 1}, nc * fri::PARTS, s, 256);
           pb_launch("open shard fin", fri::WeightedFinalK{partial, scale, d_mine, d_mine + cper}, nc, s, 64);
         }
         coll(comm->all_gather(comm->user, d_mine, d_all, 2 * cper * sizeof(E2)), "all_gather (openings)");
@@ -470,9 +506,9 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
           }
         }
       };
-      open_sharded(d_trace, W, op_tr);
+      open_sharded(tr_shard, W, op_tr);
       ch.observe_n(op_tr.data(), 2 * (size_t)W);
-      open_sharded(aux_vals, A, op_ax);
+      open_sharded(ax_shard, A, op_ax);
     } else {
       // The transcript absorbs [local | aux | quotient], [next | aux_next], [ctl_zs_first]; every batch of opened
       // values is hashed on the host while the GPU evaluates the next one (the observe ORDER is unchanged).
@@ -493,7 +529,15 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     pb_launch("open quotient fin", fri::WeightedFinalK{partial, gl::e2(1, 0), d_op, nullptr}, Q, s, 64);
     ch.observe_n(op_ax.data(), 2 * (size_t)A);  // local auxiliary values, overlapped with the quotient openings
     pb_d2h(op_q.data(), d_op, (size_t)Q * 16, s);
-    for (int k = 0; k < 2 * nch; k++) pb_d2h(&zs_first[k], aux_vals + (size_t)(nlk + k) * n, 8, s);
+    if (trace_is_block) {  // row 0 of the CTL-Z columns lives on rank 0: everyone contributes its local row 0
+      u64* z_mine = ar.alloc_n<u64>(2 * nch);
+      u64* z_all = ar.alloc_n<u64>(P * 2 * nch);
+      for (int k = 0; k < 2 * nch; k++) pb_d2d(z_mine + k, aux_vals + (size_t)(nlk + k) * nloc, 8, s);
+      coll(comm->all_gather(comm->user, z_mine, z_all, (size_t)2 * nch * 8), "all_gather (ctl_zs_first)");
+      pb_d2h(zs_first.data(), z_all, (size_t)2 * nch * 8, s);
+    } else {
+      for (int k = 0; k < 2 * nch; k++) pb_d2h(&zs_first[k], aux_vals + (size_t)(nlk + k) * n, 8, s);
+    }
     pb_sync(s);
     ar.off = mark;
   }

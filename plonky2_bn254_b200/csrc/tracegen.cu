@@ -899,7 +899,8 @@ struct ZeroPadK {  // zero rows [used, n) of every column
 };
 struct RangeCounterK {
   u64* col;
-  PB_HD void operator()(size_t i) const { col[i] = i < 65536 ? (u64)i : 65535; }
+  size_t row0;  // index of local row 0 in the whole trace (row-block form)
+  PB_HD void operator()(size_t i) const { col[i] = row0 + i < 65536 ? (u64)(row0 + i) : 65535; }
 };
 struct HistK {  // one thread per used row: frequency[v] += 1 for every range-checked cell
   const u64* trace;
@@ -995,7 +996,7 @@ static inline void run_curve(Arena& ar, const Layout& l, const u64* d_inputs, co
 }
 
 void generate(Arena& ar, int kind, const u64* d_inputs, const u64* d_ts, size_t K, size_t n_rows,
-                            u64* d_trace, int* d_err, pbStream s) {
+                            u64* d_trace, int* d_err, pbStream s, size_t row0) {
   Layout l = layout_for(kind);
   const size_t used = K * PERIOD;
   u64* rf_table = ar.alloc_n<u64>(PERIOD * 5);
@@ -1019,7 +1020,7 @@ void generate(Arena& ar, int kind, const u64* d_inputs, const u64* d_ts, size_t 
       pb_launch("tracegen fq rows", RowsFqK{B, l, d_inputs, d_ts, rf_table, d_trace, n_rows, K}, K * PERIOD, s, 64);
     }
   }
-  pb_launch("range counter", RangeCounterK{d_trace + (size_t)l.range_counter * n_rows}, n_rows, s);
+  pb_launch("range counter", RangeCounterK{d_trace + (size_t)l.range_counter * n_rows, row0}, n_rows, s);
   u64* freq = d_trace + (size_t)l.freq * n_rows;
 #if PB_HOSTSIM
   if (used > 0) pb_launch("range histogram", HistK{d_trace, freq, n_rows, l.rc_lo, l.rc_hi, d_err}, used, s, 128);

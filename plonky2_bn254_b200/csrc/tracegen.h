@@ -74,7 +74,10 @@ static inline size_t scratch_bytes(int kind, size_t K) {
 
 
 // Fills the column-major device trace (width x n_rows); errors land in *d_err (ERR_* codes).
+// row0 != 0: the matrix is the row block [row0, row0 + n_rows) of a larger trace (one proof across several GPUs):
+// the range counter continues at row0; the frequency column then holds the histogram of THIS block's cells in its
+// first 65536 rows, to be added up across the blocks by the caller (pb254.cu).
 void generate(Arena& ar, int kind, const u64* d_inputs, const u64* d_ts, size_t K, size_t n_rows, u64* d_trace,
-              int* d_err, pbStream s);
+              int* d_err, pbStream s, size_t row0 = 0);
 
 }  // namespace tg

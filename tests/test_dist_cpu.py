@@ -142,7 +142,7 @@ def _sharded_worker(rank, world, port, kind, k, rate_bits, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kind,k,rate_bits", [(2, 2, 3, 1), (4, 2, 2, 2)])
+@pytest.mark.parametrize("world,kind,k,rate_bits", [(2, 2, 130, 1), (4, 2, 2, 2)])
 def test_sharded_proof_is_the_single_rank_proof(hostsim_ctx, world, kind, k, rate_bits):
     """pb254_prove_sharded (one proof across `world` ranks: column-sharded LDE, all-to-all, row-block leaf hashing,
     row-block quotient with the next-row halo, row-block FRI combination, owner-supplied query rows) gives, on every
@@ -169,3 +169,4 @@ def test_sharded_proof_is_the_single_rank_proof(hostsim_ctx, world, kind, k, rat
         assert size == want.size and sha == hashlib.sha256(want.tobytes()).hexdigest(), f"rank {rank}"
         assert calls >= 2 * 3 + 3 and a2a > 0          # per matrix: all-to-all, digests (+ tree levels), openings; quotient, FRI, queries
         assert "exchange trace" in stages and "exchange aux" in stages
+        assert ("values exchange trace" in stages) == (k == 130)

@@ -56,7 +56,8 @@ def test_sharded_proof_over_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     world = 2
-    cases = [(2, 3, 1), (0, 130, 1), (1, 2, 1), (2, 5, 3)]   # fq; G1 at 2^17 rows; G2; fq with blow-up 8
+    cases = [(2, 3, 1), (0, 130, 1), (1, 2, 1), (2, 5, 3), (2, 300, 1), (1, 129, 1)]
+    # 2^16 rows (trace replicated): fq, G2, fq with blow-up 8; >= 2^17 rows (instance-sharded trace generation): G1, fq, G2
     port = _free_port()
     ctxmp = mp.get_context("spawn")
     q = ctxmp.Queue()
