@@ -452,7 +452,7 @@ def run_ours(args, rank, world, local_rank):
                     pf.close()
                 shas = [None] * world
                 dist.all_gather_object(shas, sha)
-                ex = sum(v for k, v in o_stage if k.startswith("exchange"))
+                ex = sum(v for k, v in o_stage if "exchange" in k)
                 oversized = {
                     "workload": f"ONE G1 proof of {inst} scalar-muls ({lib.trace_rows(inst, 1 << 16)} rows x 781 columns) "
                                 f"across {world} GPUs: column-sharded LDE, NCCL all-to-all into row blocks, row-block "
