@@ -1,7 +1,7 @@
 // GPU check + timing of the tensor-core Poseidon (csrc/poseidon_tc.cuh) against the dp2a form (csrc/poseidon.cuh)
 // and the canonical host permutation.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o bin/poseidon_tc_test poseidon_tc_test.cu
-//   ./bin/poseidon_tc_test [log2(states)] [permutations per state]
+//   ./bin/poseidon_tc_test [log2(states) | tiles of 128 states] [permutations per state]
 #include "../../plonky2_bn254_b200/csrc/poseidon_tc.cuh"
 #include <vector>
 std::atomic<unsigned long long> g_pb_launches{0};
@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(128, poseidon::tc::CTAS_PER_SM) k_tc(const u64
   } while (0)
 
 int main(int argc, char** argv) {
+  // first argument: log2(states), or (>= 64) the number of 128-state tiles
   const int lg = argc > 1 ? atoi(argv[1]) : 20, reps = argc > 2 ? atoi(argv[2]) : 8;
-  const size_t n = (size_t)1 << lg;
+  const size_t n = lg >= 64 ? (size_t)lg * 128 : (size_t)1 << lg;
   std::vector<u64> h(12 * n);
   u64 x = 0x9E3779B97F4A7C15ULL;
   for (auto& v : h) {
