@@ -170,3 +170,43 @@ def test_sharded_proof_is_the_single_rank_proof(hostsim_ctx, world, kind, k, rat
         assert calls >= 2 * 3 + 3 and a2a > 0          # per matrix: all-to-all, digests (+ tree levels), openings; quotient, FRI, queries
         assert "exchange trace" in stages and "exchange aux" in stages
         assert ("values exchange trace" in stages) == (k == 130)
+
+
+def _sharded_error_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from plonky2_bn254_b200 import build, dist as D, ffi, inputs as I
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "4"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = ffi.Context(0, library=ffi.Library(build.HOSTSIM_LIB))
+    inp, ts = I.make_inputs(I.KIND_FQ, 130, I.config_seed(72))
+    inp = inp.copy()
+    inp[129, 4:8] = np.uint64(0xFFFFFFFFFFFFFFFF)      # x >= p in an instance that only rank 1 generates
+    code = None
+    try:
+        D.prove_sharded(ctx, dist, I.KIND_FQ, inp, ts, "cpu")
+    except ffi.Pb254Error as e:
+        code = e.code
+    dist.barrier()
+    q.put((rank, code))
+    dist.destroy_process_group()
+
+
+def test_sharded_input_error_fails_on_every_rank():
+    """A non-canonical coordinate in an instance of rank 1's block: the error code is all-gathered after trace
+    generation, so rank 0 returns PB254_E_NOT_CANONICAL too instead of waiting in the next collective."""
+    from plonky2_bn254_b200 import build
+    build.build_hostsim()
+    world, port = 2, _free_port()
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    procs = [ctxmp.Process(target=_sharded_error_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, 3), (1, 3)]
