@@ -75,6 +75,17 @@ pub struct pb254_proof_layout {
     pub q_step_path_words: [u32; PB254_MAX_FRI_LAYERS],
 }
 
+/// `pb254_comm` (include/pb254.h): the caller's collectives for ONE proof across the GPUs of a node. The callbacks get
+/// device pointers on the context's GPU and must enqueue on (or order with) the context's stream; 0 = success.
+#[repr(C)]
+pub struct pb254_comm {
+    pub rank: u32,
+    pub world: u32,
+    pub user: *mut c_void,
+    pub all_to_all: Option<unsafe extern "C" fn(user: *mut c_void, d_send: *const c_void, d_recv: *mut c_void, bytes_per_peer: usize) -> c_int>,
+    pub all_gather: Option<unsafe extern "C" fn(user: *mut c_void, d_send: *const c_void, d_recv: *mut c_void, bytes_per_rank: usize) -> c_int>,
+}
+
 #[repr(C)]
 pub struct pb254_ctx {
     _private: [u8; 0],
@@ -111,6 +122,12 @@ extern "C" {
                            out: *mut *mut pb254_proof) -> c_int;
     pub fn pb254_prove_trace(ctx: *mut pb254_ctx, kind: c_int, trace_cols: *const u64, n_rows: usize,
                              cfg: *const pb254_config, keep_debug: c_int, out: *mut *mut pb254_proof) -> c_int;
+    pub fn pb254_prove_many(ctxs: *const *mut pb254_ctx, n_ctx: usize, kind: c_int, inputs: *const u64, timestamps: *const u64,
+                            n_inputs: usize, n_batches: usize, min_rows: usize, cfg: *const pb254_config,
+                            proofs_out: *mut *mut pb254_proof) -> c_int;
+    pub fn pb254_prove_sharded(ctx: *mut pb254_ctx, kind: c_int, inputs: *const u64, timestamps: *const u64, n_inputs: usize,
+                               min_rows: usize, cfg: *const pb254_config, comm: *const pb254_comm,
+                               out: *mut *mut pb254_proof) -> c_int;
     pub fn pb254_proof_free(proof: *mut pb254_proof);
     pub fn pb254_verify(kind: c_int, cfg: *const pb254_config, proof_words: *const u64, n_words: usize,
                         inputs: *const u64, timestamps: *const u64, n_inputs: usize) -> c_int;

@@ -177,6 +177,32 @@ impl Context {
         Self::take(h)
     }
 
+    /// ONE proof across the GPUs of a node (`pb254_prove_sharded`): every rank (one process per GPU) calls this with the
+    /// same `words` / `timestamps` and its own collectives - e.g. closures over an NCCL communicator created on the
+    /// stream this context was created with. All ranks return the same proof, byte-identical to `prove` on one GPU.
+    /// (No native outputs in this mode: the trace is spread over the ranks.)
+    pub fn prove_sharded(&self, kind: i32, words: &[u64], timestamps: &[u64], min_rows: usize, config: Option<&StarkConfig>,
+                         rank: u32, world: u32, collectives: &mut dyn Collectives) -> Result<Proved> {
+        unsafe extern "C" fn a2a(user: *mut std::ffi::c_void, s: *const std::ffi::c_void, r: *mut std::ffi::c_void, n: usize) -> i32 {
+            let c = &mut **(user as *mut &mut dyn Collectives);
+            c.all_to_all(s as *const u8, r as *mut u8, n).map_or(1, |_| 0)
+        }
+        unsafe extern "C" fn ag(user: *mut std::ffi::c_void, s: *const std::ffi::c_void, r: *mut std::ffi::c_void, n: usize) -> i32 {
+            let c = &mut **(user as *mut &mut dyn Collectives);
+            c.all_gather(s as *const u8, r as *mut u8, n).map_or(1, |_| 0)
+        }
+        let cfg = config.map(config_of).transpose()?;
+        let mut fat: &mut dyn Collectives = collectives;
+        let comm = sys::pb254_comm { rank, world, user: &mut fat as *mut _ as *mut std::ffi::c_void,
+                                     all_to_all: Some(a2a), all_gather: Some(ag) };
+        let mut h = std::ptr::null_mut();
+        check(unsafe {
+            sys::pb254_prove_sharded(self.0, kind, words.as_ptr(), timestamps.as_ptr(), timestamps.len(), min_rows,
+                                     cfg.as_ref().map_or(std::ptr::null(), |c| c as *const _), &comm, &mut h)
+        })?;
+        Self::take(h)
+    }
+
     /// `generate_trace` alone: column-major `width x rows` (the transpose `trace_rows_to_poly_values` builds).
     pub fn generate_trace(&self, kind: i32, words: &[u64], timestamps: &[u64], min_rows: usize) -> Result<Vec<Vec<F>>> {
         let width = unsafe { sys::pb254_trace_width(kind) } as usize;
@@ -277,4 +303,29 @@ pub fn decode_proof(blob: &[u64]) -> Result<StarkProofWithMetadata<F, C, D>> {
         opening_proof,
     };
     Ok(StarkProofWithMetadata { init_challenger_state, proof })
+}
+
+
+/// The two collectives `Context::prove_sharded` needs, on DEVICE pointers of the context's GPU (sizes in bytes).
+/// `all_to_all`: `world` chunks of `bytes_per_peer`, chunk q goes to rank q, chunk q of `recv` came from rank q;
+/// `all_gather`: `recv` = `world` chunks of `bytes_per_rank` in rank order. Enqueue on the context's stream.
+pub trait Collectives {
+    fn all_to_all(&mut self, d_send: *const u8, d_recv: *mut u8, bytes_per_peer: usize) -> Result<()>;
+    fn all_gather(&mut self, d_send: *const u8, d_recv: *mut u8, bytes_per_rank: usize) -> Result<()>;
+}
+
+/// A stream of independent batches through several contexts of one GPU (`pb254_prove_many`): batch b is proved on
+/// `contexts[b % contexts.len()]` by the library's own host threads; proofs come back in batch order.
+/// `words`: the batches' `pack_*` rows back to back, `timestamps`: `n_batches * n_inputs` values.
+pub fn prove_many(contexts: &[&Context], kind: i32, words: &[u64], timestamps: &[u64], n_inputs: usize, min_rows: usize,
+                  config: Option<&StarkConfig>) -> Result<Vec<Proved>> {
+    let n_batches = timestamps.len() / n_inputs;
+    let cfg = config.map(config_of).transpose()?;
+    let ctxs: Vec<*mut sys::pb254_ctx> = contexts.iter().map(|c| c.0).collect();
+    let mut handles = vec![std::ptr::null_mut(); n_batches];
+    check(unsafe {
+        sys::pb254_prove_many(ctxs.as_ptr(), ctxs.len(), kind, words.as_ptr(), timestamps.as_ptr(), n_inputs, n_batches, min_rows,
+                              cfg.as_ref().map_or(std::ptr::null(), |c| c as *const _), handles.as_mut_ptr())
+    })?;
+    handles.into_iter().map(Context::take).collect()
 }
