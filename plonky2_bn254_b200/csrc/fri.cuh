@@ -82,6 +82,19 @@ struct WeightedPartialK {
     o[3] = b1.reduce();
   }
 };
+// The 1024 partial sums of a column are added up in two steps (32 x 32) so that the second step is not one thread
+// per column walking 4096 words: WeightedMidK leaves the sum of partials [32 g, 32 g + 32) in slot 32 g.
+static constexpr int MID = 32;
+struct WeightedMidK {
+  u64* partial;
+  PB_HD void operator()(size_t gid) const {  // gid = col * (PARTS / MID) + g
+    u64* p = partial + gid * MID * 4;
+    u64 s[4] = {0, 0, 0, 0};
+    for (int q = 0; q < MID; q++)
+      for (int k = 0; k < 4; k++) s[k] = gl::add(s[k], p[q * 4 + k]);
+    for (int k = 0; k < 4; k++) p[k] = s[k];
+  }
+};
 struct WeightedFinalK {
   const u64* partial;
   E2 scale;
@@ -89,12 +102,16 @@ struct WeightedFinalK {
   E2* out_next;  // [ncols] or null
   PB_HD void operator()(size_t col) const {
     u64 s[4] = {0, 0, 0, 0};
-    for (int p = 0; p < PARTS; p++)
+    for (int p = 0; p < PARTS; p += MID)
       for (int k = 0; k < 4; k++) s[k] = gl::add(s[k], partial[(col * PARTS + p) * 4 + k]);
     out[col] = gl::emul(gl::e2(s[0], s[1]), scale);
     if (out_next) out_next[col] = gl::emul(gl::e2(s[2], s[3]), scale);
   }
 };
+static inline void finish_openings(u64* partial, size_t ncols, E2 scale, E2* out, E2* out_next, pbStream s) {
+  pb_launch("open mid", WeightedMidK{partial}, ncols * (PARTS / MID), s, 128);
+  pb_launch("open fin", WeightedFinalK{partial, scale, out, out_next}, ncols, s, 64);
+}
 
 // ---- K10 combine -----------------------------------------------------------------------------
 struct CombineK {
@@ -116,12 +133,14 @@ struct CombineK {
     const size_t i = i_base + il;
     const u64 x = gl::mul(gl::COSET_SHIFT, ntt::tpow(t.fwd_lo, t.fwd_hi, (u64)i << (ntt::LOG_M - log_N)));
     gl::Acc sa, sb, fa, fb;
+#pragma unroll 4
     for (int c = 0; c < W; c++) {
       u64 v = tr[(size_t)c * tr_stride + il];
       E2 a = apow[c];
       sa.mac(a.a, v);
       sb.mac(a.b, v);
     }
+#pragma unroll 4
     for (int c = 0; c < A; c++) {
       u64 v = ax[(size_t)c * ax_stride + il];
       E2 a = apow[W + c];

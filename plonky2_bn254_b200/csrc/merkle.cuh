@@ -86,37 +86,7 @@ __device__ __forceinline__ void stage_rc2(u64* rc2) {
   __syncthreads();
 }
 
-// one thread per LDE row
-__global__ void __launch_bounds__(128, 6) k_leaf_hash(const u64* __restrict__ lde, size_t stride, int W, int log_n,
-                                                   Digest* __restrict__ out, size_t rows, int natural) {
-  __shared__ __align__(16) u64 rc2[poseidon::RC2_WORDS];
-  stage_rc2(rc2);
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= rows) return;
-  const u64* p = lde + j;
-  u64 s[12];
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = 0;
-  const int chunks = (W + 7) / 8;
-  // No software prefetch: a warp spends ~10^5 cycles in one permutation, three orders of magnitude more than
-  // the latency of the 8 loads in front of it, and the 16 registers are worth more than the overlap.
-#pragma unroll 1
-  for (int c = 0; c < chunks; c++) {
-    // hash_no_pad overwrites the first min(8, remaining) rate lanes with the chunk
-    const int len = W - 8 * c;
-    const u64* q = p + (size_t)c * 8 * stride;
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (k < len) s[k] = q[(size_t)k * stride];
-    poseidon::lazy::permute(s, rc2);
-  }
-  Digest d;
-#pragma unroll
-  for (int i = 0; i < 4; i++) d.e[i] = s[i];
-  out[natural ? j : (size_t)gl::brev32((u32)j, log_n)] = d;
-}
-
-// Same kernel with the MDS layers on the tensor cores (poseidon_tc.cuh): one CTA = 128 rows = the 128 rows of the
+// One thread per LDE row, the MDS layers on the tensor cores (poseidon_tc.cuh): one CTA = 128 rows = the 128 rows of the
 // u8 x u8 -> s32 product. Every thread takes part in every permutation (the CTA-wide barrier and the TMEM loads are
 // collective), rows past the end hash row 0 and drop the result.
 __global__ void __launch_bounds__(poseidon::tc::CTA, poseidon::tc::CTAS_PER_SM)

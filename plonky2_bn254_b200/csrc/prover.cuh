@@ -492,7 +492,7 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
         pb_memset(d_mine, 0, 2 * cper * sizeof(E2), s);
         if (nc) {
           pb_launch("open shard", fri::WeightedPartialK{shard, n, n, wz, partial, 1}, nc * fri::PARTS, s, 256);
-          pb_launch("open shard fin", fri::WeightedFinalK{partial, scale, d_mine, d_mine + cper}, nc, s, 64);
+          fri::finish_openings(partial, nc, scale, d_mine, d_mine + cper, s);
         }
         coll(comm->all_gather(comm->user, d_mine, d_all, 2 * cper * sizeof(E2)), "all_gather (openings)");
         std::vector<u64> h(P * 4 * cper);
@@ -514,11 +514,11 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
       // values is hashed on the host while the GPU evaluates the next one (the observe ORDER is unchanged).
       E2* d_op2 = ar.alloc_n<E2>(2 * WA);
       pb_launch("open trace", fri::WeightedPartialK{d_trace, n, n, wz, partial, 1}, (size_t)W * fri::PARTS, s, 256);
-      pb_launch("open trace fin", fri::WeightedFinalK{partial, scale, d_op, d_op + W}, W, s, 64);
+      fri::finish_openings(partial, W, scale, d_op, d_op + W, s);
       pb_d2h(op_tr.data(), d_op, (size_t)W * 32, s);
       pb_sync(s);
       pb_launch("open aux", fri::WeightedPartialK{aux_vals, n, n, wz, partial, 1}, (size_t)A * fri::PARTS, s, 256);
-      pb_launch("open aux fin", fri::WeightedFinalK{partial, scale, d_op2, d_op2 + A}, A, s, 64);
+      fri::finish_openings(partial, A, scale, d_op2, d_op2 + A, s);
       // (host hashing comes before the copy: a device-to-host copy into pageable memory blocks the host)
       ch.observe_n(op_tr.data(), 2 * (size_t)W);  // local trace values, overlapped with the auxiliary openings
       pb_d2h(op_ax.data(), d_op2, (size_t)A * 32, s);
@@ -526,7 +526,7 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     }
     pb_launch("zeta powers", fri::PowTableK{wz, zeta}, n, s, 128);
     pb_launch("open quotient", fri::WeightedPartialK{qcoef, n, n, wz, partial, 0}, (size_t)Q * fri::PARTS, s, 256);
-    pb_launch("open quotient fin", fri::WeightedFinalK{partial, gl::e2(1, 0), d_op, nullptr}, Q, s, 64);
+    fri::finish_openings(partial, Q, gl::e2(1, 0), d_op, nullptr, s);
     ch.observe_n(op_ax.data(), 2 * (size_t)A);  // local auxiliary values, overlapped with the quotient openings
     pb_d2h(op_q.data(), d_op, (size_t)Q * 16, s);
     if (trace_is_block) {  // row 0 of the CTL-Z columns lives on rank 0: everyone contributes its local row 0
