@@ -59,3 +59,23 @@ def test_lde_linearity_large(gpu_ctx):
     la, lb, lab = (gpu_ctx.lde_batch(x, 1) for x in (a, b, addmod(a, b)))
     assert (addmod(la, lb) == lab).all()
     # the LDE on the even coset points restricted ... spot check: value 0 equals P(7) by Horner over few coeffs
+
+
+@pytest.mark.parametrize("cols,rows,stride", [(21, 1000, 1024), (8, 129, 129), (5, 1, 7), (4, 300, 300)])
+def test_leaf_hash_of_ragged_row_blocks(gpu_ctx, oracle, cols, rows, stride):
+    """pb254_leaf_hash_rows_dev (the row-block form the sharded prover uses; on the device the tensor-core kernel, one
+    CTA per 128 rows): row counts that are not a multiple of 128, a stride larger than the row count, a width that is
+    not a multiple of the sponge rate, and the <= 4 column no-hash case - each digest against the oracle's hash."""
+    import torch
+    rng = np.random.default_rng(cols * 1000 + rows)
+    m = rand_field(rng, (cols, stride))
+    d_m = torch.from_numpy(m.view(np.int64)).cuda()
+    d_out = torch.zeros((rows, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()  # the context has its own (non-blocking) stream
+    gpu_ctx.leaf_hash_rows_dev(d_m.data_ptr(), stride, cols, rows, d_out.data_ptr())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint64)
+    for i in sorted(set([0, 1, 127, 128, rows - 1, rows // 2]) & set(range(rows))):
+        row = m[:, i]
+        want = oracle.hash_no_pad(row) if cols > 4 else np.concatenate([row, np.zeros(4 - cols, dtype=np.uint64)])
+        assert (got[i] == want).all(), i
