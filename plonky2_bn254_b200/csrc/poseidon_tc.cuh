@@ -152,14 +152,24 @@ __device__ __forceinline__ u64 recombine4(u32 acc0, u32 acc1, u32 acc2, u32 acc3
   return ((u64)hi << 32) | lo;
 }
 
+// The eight byte-weight sums a_q < 2^17.1 of one lane -> a lazy u64 representative of sum a_q 2^(8 q).
+__device__ __forceinline__ u64 fold8(const u32* q) {
+  return recombine4(q[0] + (q[1] << 8), q[2] + (q[3] << 8), q[4] + (q[5] << 8), q[6] + (q[7] << 8));
+}
+
 // Measured and dropped (tools/microbench/poseidon_tc_test.cu, 2^20 states x 16 permutations; this form: 1.246 Gperm/s,
 // the dp2a form 1.09): one 128-column allocation and one N = 96 product per K step with four CTAs per SM (1.20); one
 // persistent CTA of 4 or 5 groups of 128 threads on named barriers owning all 512 columns (1.20 / 1.16, top stall
 // `barrier`); one TMEM wait for all 96 columns (1.22); the fold in plain 128-bit integer code (ptxas moves a third
 // of it to the FMA pipe but emits 23 instead of 19 instructions: 1.13); the wrap correction of the multiplication on
 // the FMA pipe (1.23); twelve S-boxes unrolled (1.25, not worth the code); the S-box of a partial round interleaved
-// with the folds of the other eleven lanes (1.24). ncu (profiles/): 18.1 k thread-instructions per permutation against
-// 24.5 k, issue slots 64 % busy, ALU pipe 71 %, FMA pipe 24 %, tensor pipe 20 %.
+// with the folds of the other eleven lanes (1.24); a fold that ptxas keeps on the FMA pipe (four IMAD and three
+// IMAD.WIDE with the running value as 64-bit addend, 15 instructions with 8 on the ALU pipe instead of 19 with 17: 1.257
+// against 1.264 on 8140 tiles) - i.e. neither the ALU pipe nor the instruction count binds: with five warps per
+// scheduler the kernel is bound by the latency of its serial phases (S-box chain, barrier, product round trip, TMEM
+// load). ncu (profiles/): 18.1 k thread-instructions per permutation against 24.5 k, issue slots 64 % busy, ALU pipe
+// 71 %, FMA pipe 24 %, tensor pipe 20 %; 128-row tiles beyond a whole number of waves cost little (8192 tiles on 740
+// CTA slots: +1.6 % time for +0.6 % work, the lone CTAs of the last wave run faster).
 
 // s <- MDS s + constants of round L + 1, all 128 threads of the CTA together
 __device__ __forceinline__ void mds_layer(u64 s[12], Ctx& c, int L) {
@@ -206,7 +216,7 @@ __device__ __forceinline__ void mds_layer(u64 s[12], Ctx& c, int L) {
 #define PB_TC_FOLD(a, base)                                                                                   \
   _Pragma("unroll") for (int r = 0; r < 4; r++) {                                                             \
     const u32* q = a + 8 * r;                                                                                 \
-    s[base + r] = recombine4(q[0] + (q[1] << 8), q[2] + (q[3] << 8), q[4] + (q[5] << 8), q[6] + (q[7] << 8)); \
+    s[base + r] = fold8(q);                                                                                   \
   }
     // the next 32 columns are in flight while the previous 32 are folded
     u32 a[32], b[32];
