@@ -51,6 +51,9 @@ static inline void pb_copy2d(void* d, size_t dpitch, const void* s_, size_t spit
 }
 static inline void pb_sync(pbStream) {}
 static inline void pb_set_device(int) {}
+struct PbDeviceGuard {
+  explicit PbDeviceGuard(int) {}
+};
 
 extern std::atomic<unsigned long long> g_pb_launches;
 template <class F>
@@ -106,6 +109,20 @@ static inline void pb_copy2d(void* d, size_t dpitch, const void* s_, size_t spit
 }
 static inline void pb_sync(pbStream s) { PB_CUDA(cudaStreamSynchronize(s)); }
 static inline void pb_set_device(int d) { PB_CUDA(cudaSetDevice(d)); }
+// An entry point works on its context's device and leaves the CALLER's current device as it found it (the host
+// language - torch, a Rust CUDA binding - keeps its own notion of the current device).
+struct PbDeviceGuard {
+  int prev = -1;
+  explicit PbDeviceGuard(int d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != d) PB_CUDA(cudaSetDevice(d));
+  }
+  ~PbDeviceGuard() {
+    if (prev >= 0) (void)cudaSetDevice(prev);
+  }
+  PbDeviceGuard(const PbDeviceGuard&) = delete;
+  PbDeviceGuard& operator=(const PbDeviceGuard&) = delete;
+};
 
 // launch counter (reported by bench.py as gpu_launches)
 extern std::atomic<unsigned long long> g_pb_launches;

@@ -130,7 +130,7 @@ uint64_t pb254_launch_count(void) { return g_pb_launches.load(); }
 int pb254_ctx_create(int device, void* stream, pb254_ctx** out) {
   return guarded([&] {
     if (!out) throw Pb254Error(PB254_E_BAD_ARG, "null out pointer");
-    pb_set_device(device);
+    PbDeviceGuard device_guard(device);
     pb254_ctx* c = new pb254_ctx();
     c->device = device;
 #if PB_HOSTSIM
@@ -185,7 +185,7 @@ size_t pb254_trace_rows(size_t n_inputs, size_t min_rows) {
 int pb254_poseidon_permute(pb254_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
   return guarded([&] {
     need_ctx(c);
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     c->arena.reserve(2 * n * 96 + 1024);
     c->arena.reset();
     u64* din = c->arena.alloc_n<u64>(n * 12);
@@ -201,7 +201,7 @@ int pb254_lde_batch(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n,
                     uint64_t* lde_out) {
   return guarded([&] {
     need_ctx(c);
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     int L = ilog2_strict(n);
     size_t N = n << rate_bits;
     c->arena.reserve((2 * cols * n + cols * N) * 8 + 4096);
@@ -221,7 +221,7 @@ int pb254_commit(pb254_ctx* c, const uint64_t* values, size_t cols, size_t n, ui
                  int from_coeffs, uint64_t* cap_out, uint64_t* digests_out) {
   return guarded([&] {
     need_ctx(c);
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     int L = ilog2_strict(n);
     size_t N = n << rate_bits;
     int log_N = L + (int)rate_bits;
@@ -255,7 +255,7 @@ int pb254_generate_trace(pb254_ctx* c, int kind, const uint64_t* inputs, const u
     need_ctx(c);
     need_kind(kind);
     need(inputs && timestamps && cols_out && n_inputs > 0, "null or empty argument");
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     tg::Layout l = tg::layout_for(kind);
     size_t n_rows = pb254_trace_rows(n_inputs, min_rows);
     need_trace_rows(n_rows);
@@ -292,7 +292,7 @@ static int prove_inputs_impl(pb254_ctx* c, int kind, const uint64_t* inputs, con
     need_ctx(c);
     need_kind(kind);
     need(inputs && timestamps && n_inputs > 0, "null or empty input");
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     tg::Layout l = tg::layout_for(kind);
     size_t n_rows = pb254_trace_rows(n_inputs, min_rows);
     const pb254_config cfg = config_or_default(cfg_in, need_trace_rows(n_rows));
@@ -367,7 +367,7 @@ int pb254_prove_sharded(pb254_ctx* c, int kind, const uint64_t* inputs, const ui
     need_kind(kind);
     need(inputs && timestamps && n_inputs > 0, "null or empty input");
     need(comm->rank < comm->world && comm->all_to_all && comm->all_gather, "comm: rank < world, callbacks non-null");
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     const tg::Layout l = tg::layout_for(kind);
     const size_t n_rows = pb254_trace_rows(n_inputs, min_rows), P = comm->world, rk = comm->rank, nloc = n_rows / P;
     const pb254_config cfg = config_or_default(cfg_in, need_trace_rows(n_rows));
@@ -485,7 +485,7 @@ int pb254_prove_trace(pb254_ctx* c, int kind, const uint64_t* trace_cols, size_t
     need_ctx(c);
     need_kind(kind);
     need(trace_cols != nullptr, "null trace");
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     const pb254_config cfg = config_or_default(cfg_in, need_trace_rows(n_rows));
     tg::Layout l = tg::layout_for(kind);
     size_t twords = (size_t)l.width * n_rows;
@@ -527,7 +527,7 @@ int pb254_lde_dev(pb254_ctx* c, const uint64_t* d_values, size_t cols, size_t n,
                   uint64_t* d_lde_out) {
   return guarded([&] {
     need_ctx(c);
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     int L = ilog2_strict(n);
     c->arena.reserve(cols * n * 8 + 4096);
     c->arena.reset();
@@ -546,7 +546,7 @@ int pb254_leaf_hash_rows_dev(pb254_ctx* c, const uint64_t* d_matrix, size_t stri
                              uint64_t* d_digests_out) {
   return guarded([&] {
     need_ctx(c);
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     c->times.clear();
     int t0 = c->times.begin("leaf hash rows", c->stream);
     merkle::hash_rows_natural(d_matrix, stride, (int)cols, rows, (merkle::Digest*)d_digests_out, c->stream);
@@ -562,7 +562,7 @@ int pb254_merkle_subtree_dev(pb254_ctx* c, const uint64_t* d_all_digests, uint32
                              uint32_t log_sub, uint32_t log_roots, uint64_t* d_roots_out) {
   return guarded([&] {
     need_ctx(c);
-    pb_set_device(c->device);
+    PbDeviceGuard device_guard(c->device);
     if (log_roots > log_sub || log_sub > log_total) throw Pb254Error(PB254_E_BAD_ARG, "subtree shape");
     size_t nd = merkle::tree_digests((int)log_sub, (int)log_roots);
     c->arena.reserve(nd * 32 + 4096);

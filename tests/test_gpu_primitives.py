@@ -69,8 +69,8 @@ def test_leaf_hash_of_ragged_row_blocks(gpu_ctx, oracle, cols, rows, stride):
     import torch
     rng = np.random.default_rng(cols * 1000 + rows)
     m = rand_field(rng, (cols, stride))
-    d_m = torch.from_numpy(m.view(np.int64)).cuda()
-    d_out = torch.zeros((rows, 4), dtype=torch.int64, device="cuda")
+    d_m = torch.from_numpy(m.view(np.int64)).to("cuda:0")   # the device of the gpu_ctx fixture
+    d_out = torch.zeros((rows, 4), dtype=torch.int64, device="cuda:0")
     torch.cuda.synchronize()  # the context has its own (non-blocking) stream
     gpu_ctx.leaf_hash_rows_dev(d_m.data_ptr(), stride, cols, rows, d_out.data_ptr())
     torch.cuda.synchronize()

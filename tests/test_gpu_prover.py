@@ -121,10 +121,13 @@ def test_second_device_in_the_same_process(gpu_ctx):
         pytest.skip("needs two GPUs")
     inp, ts = I.make_inputs(I.KIND_FQ, 2, I.config_seed(95))
     a = gpu_ctx.prove(I.KIND_FQ, inp, ts).words()
+    before = torch.cuda.current_device()
     ctx1 = ffi.Context(1)
     b = ctx1.prove(I.KIND_FQ, inp, ts).words()
     ctx1.close()
     assert (a == b).all()
+    # the entry points leave the caller's current device as they found it
+    assert torch.cuda.current_device() == before
 
 
 def test_prove_many(gpu_ctx):
