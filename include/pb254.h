@@ -115,7 +115,11 @@ int pb254_merkle_subtree_dev(pb254_ctx* ctx, const uint64_t* d_all_digests, uint
  *   quotient evaluation             row blocks of the LDE with a next-row halo -> all_gather of the values
  *   FRI combination                 row blocks -> all_gather
  *   query openings                  rows from the rank that owns them -> all_gather
- * and the proof is byte-identical to the single-GPU proof on every rank. The collectives are the CALLER's (its own
+ *   trace generation, auxiliary     by instances / row blocks when n / world is a multiple of 512 and >= 2^16 (every
+ *   columns                         BASELINE size), with one all_to_all of values per matrix; replicated otherwise
+ * and the proof is byte-identical to the single-GPU proof on every rank (pb254_proof_results_* is empty when the trace
+ * is generated by instances: the native outputs are then spread over the ranks). An input error of any instance fails
+ * the call on EVERY rank with the same code. The collectives are the CALLER's (its own
  * NCCL communicator: torch.distributed in plonky2_bn254_b200/dist.py, an NCCL binding in a Rust caller): the library
  * calls back with device pointers on the context's GPU; the callee must enqueue the collective on the context's
  * stream (or order it after prior and before later work of that stream) and return 0 on success. */
