@@ -377,7 +377,17 @@ int pb254_prove_sharded(pb254_ctx* c, int kind, const uint64_t* inputs, const ui
     const size_t twords = Wpad * nloc;
     size_t tg_bytes = tg::scratch_bytes(kind, kloc ? kloc : 1) + (kloc + 1) * (l.in_words + 1) * 8 + (P + 1) * 65536 * 8 + 65536;
     size_t pv_bytes = prover::workspace_bytes_sharded(kind, n_rows, cfg, P);
-    c->arena.reserve(twords * 8 + (tg_bytes > pv_bytes ? tg_bytes : pv_bytes) + 65536);
+    size_t want = twords * 8 + (tg_bytes > pv_bytes ? tg_bytes : pv_bytes) + 65536;
+#if !PB_HOSTSIM
+    {  // the estimate is an upper bound: never ask for more than the device has left (the collectives of the caller
+       // need room too); a proof that really does not fit fails in Arena::alloc with PB254_E_OOM
+      size_t free_b = 0, total_b = 0;
+      PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const size_t avail = free_b + c->arena.cap, margin = (size_t)4 << 30;
+      if (avail > margin && want > avail - margin) want = avail - margin;
+    }
+#endif
+    c->arena.reserve(want);
     c->arena.reset();
     c->times.clear();
     u64* d_rows = c->arena.alloc_n<u64>(twords);

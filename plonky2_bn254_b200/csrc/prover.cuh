@@ -105,6 +105,7 @@ static inline size_t workspace_bytes_sharded(int kind, size_t n, const pb254_con
   size_t words = (W + A + 2 * world) * (Nloc + halo) + Q * N    // row blocks, quotient LDE
                  + cper * n + A * n                             // NTT scratch, aux values
                  + cper * N + Cpad * (Nloc + halo)                 // column-shard LDE, send buffer
+                 + 3 * cper * n                                    // value column shards (trace, aux) + their exchange
                  + 4 * (Nloc + N)                               // digests of the own rows, of all rows
                  + 4 * nch * n * 2 + 2 * nch * n + (nch << 16) + 4 * nch * (n / 256 + 16) + 2 * n
                  + WA * fri::PARTS * 4 + 6 * (W + A + Q) + 3 * N + 2 * Nloc + 2 * N
