@@ -16,8 +16,13 @@ section 8d "config 2"), StarkConfig::standard_fast_config(). Synthetic inputs: S
   cpu_baseline the CPU oracle (a restatement of the reference prover; the Rust crate cannot be built
                offline) on a bounded sample, timed on this box's host cores
 
-N > 1 (torchrun): independent proof batches per GPU (replicas, SURVEY.md 8e) - no data-path collective;
-the NCCL process group is only used for the barrier and the max-over-ranks time.
+  other_configs    BASELINE configs 3 (G2 x 1024) and 4 (fq_exp x 4096, blow-up 8), measured in the same run
+  pipelined        pb254_prove_many: a stream of proofs through two contexts of the same GPU
+  oversized_trace  N > 1 only: BASELINE config 5, ONE proof of 2^22 rows across all N GPUs (pb254_prove_sharded:
+                   column-sharded LDE, NCCL all-to-all, row-block hashing / quotient / FRI combination)
+
+N > 1 (torchrun): independent proof batches per GPU (replicas) - no data-path collective for the
+headline value; the NCCL process group is used for the barrier, the max-over-ranks time and the oversized proof.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port, all host threads) on a bounded
 sample of the same workload; this and the cpu_baseline leg are the only places bench.py executes oracle/.
