@@ -15,13 +15,14 @@
 //                            round's constant of lane r (so the constant addition rides along); constant, 12 KB
 //   D [128 states x  96 n]   s32 in tensor memory: D[t][8 r + q'] = sum_i MDS[r][i] byte_q'(s_i) + rc byte < 2^17
 //
-// four tcgen05.mma.kind::i8 (M 128, N 96, K 32) per layer, issued by one thread, completion through an mbarrier;
+// tcgen05.mma.kind::i8 products (M 128, K 32 per instruction: four K steps, each as an N = 64 and an N = 32 half, see
+// CTAS_PER_SM below) per layer, issued by one thread, completion through an mbarrier;
 // every thread then reads its own row of D with tcgen05.ld (TMEM lane = state = thread), folds the eight byte-weight
 // sums of each lane into a lazy u64 representative (4 shift-adds + the 15-instruction piece recombination of the
 // dp2a form) and goes on with the S-boxes. Per layer and thread: 8 shared-memory stores, 1 barrier, 3 TMEM loads
 // and ~230 ALU instructions instead of ~500, and the FMA pipe is left to the S-box multiplications.
-// Four CTAs per SM (4 x 128 TMEM columns, 4 x 28 KB shared memory) hide the MMA round trip of one CTA behind the
-// S-boxes and recombinations of the others.
+// Five CTAs per SM (5 x (64 + 32) TMEM columns, 5 x 29 KB shared memory) hide the MMA round trip of one CTA behind
+// the S-boxes and recombinations of the others.
 #pragma once
 #include "poseidon.cuh"
 
