@@ -349,6 +349,22 @@ struct StridedArgs {
   Rounds R;
   const u64* tw;   // in-tile twiddles (R.words)
   const u64* tw4;  // four-step table, same [row][c] layout as one column
+  // Row-block output of pass D (one proof across several GPUs, prover.cuh commit_sharded): row r of column `by` goes
+  // to chunk r >> rb_log (the rank that will own the row) at out + chunk * rb_chunk_words + by * rb_col_stride +
+  // (r mod 2^rb_log), and the first rb_halo rows of every chunk are repeated behind the previous chunk's rows (its
+  // next-row halo, wrapping around) - the send buffer of the all-to-all is written by the transform itself instead
+  // of by a pack copy. rb_log == 0: plain column-major output.
+  int rb_log = 0;
+  unsigned rb_chunks = 0;
+  size_t rb_col_stride = 0, rb_chunk_words = 0, rb_halo = 0;
+};
+struct RowBlocks {
+  u64* dst;
+  int log_rows;         // rows per chunk = 2^log_rows
+  unsigned chunks;
+  size_t col_stride;    // words between columns inside a chunk (rows per chunk + halo)
+  size_t chunk_words;   // words between chunks
+  size_t halo;
 };
 
 // INV: pass A (DIF, inverse roots; last round multiplies by tw4 and stores to `out`, any representatives).
@@ -399,7 +415,19 @@ PB_D void strided_body(u64* sm, unsigned bx, unsigned by, int nt, const StridedA
           else
             radix_item_34<true>(lq, u, lstep, ld, tw_tile, st_tile);
         } else {
-          auto st_out = [&](int slot, u64 v) { dst[((size_t)slot << lrs) + c] = canon(v); };
+          auto st_out = [&](int slot, u64 v) {
+            const u64 cv = canon(v);
+            if (a.rb_log) {
+              const size_t row = ((size_t)slot << lrs) + (size_t)bx * TC + c;
+              const size_t q = row >> a.rb_log, off = row & (((size_t)1 << a.rb_log) - 1);
+              u64* base = a.out + (size_t)by * a.rb_col_stride;
+              base[q * a.rb_chunk_words + off] = cv;
+              if (off < a.rb_halo)
+                base[((q + a.rb_chunks - 1) % a.rb_chunks) * a.rb_chunk_words + ((size_t)1 << a.rb_log) + off] = cv;
+            } else {
+              dst[((size_t)slot << lrs) + c] = cv;
+            }
+          };
           if (first && last)
             radix_item_34<false>(lq, u, lstep, ld, tw_four, st_out);
           else if (first)
@@ -653,9 +681,12 @@ static inline void check_align(const void* p, size_t stride) {
 // mode FROM_VALUES_LDE / FROM_COEFFS_LDE: LDE of `ncols` columns. in: [col][in_stride] (n used), out: [col][out_stride]
 // (N = n << r used). mode INTT_COSET_NAT (r must be 0): natural-order values on 7 <w> -> natural-order coefficients.
 // scratch: at least ncols * n words (unused when K1 == 0 or in FROM_COEFFS mode). out may not alias in.
-static inline void transform_columns(TableSet& ts, const u64* in, size_t in_stride, u64* out, size_t out_stride, u64* scratch,
-                                     int ncols, int L, int r, int mode, pbStream s) {
-  if (ncols == 0) return;
+// rb (LDE modes only): the last pass writes the result in row-block layout to rb->dst instead of column-major to
+// `out` (which is then only the intermediate buffer); returns false - and ignores rb - when the transform is too small
+// to have a strided last pass, the caller then repacks `out` itself.
+static inline bool transform_columns(TableSet& ts, const u64* in, size_t in_stride, u64* out, size_t out_stride, u64* scratch,
+                                     int ncols, int L, int r, int mode, pbStream s, const RowBlocks* rb = nullptr) {
+  if (ncols == 0) return rb != nullptr;
   const size_t n = (size_t)1 << L;
 #if !PB_HOSTSIM
   set_smem_attrs();
@@ -680,13 +711,29 @@ static inline void transform_columns(TableSet& ts, const u64* in, size_t in_stri
   }
   if (mode != INTT_COSET_NAT && p.K1 > 0) {
     StridedArgs a = {out, out, out_stride, out_stride, p.K1, p.Kc + r, p.d, p.tw_d, p.tw4_d};
+    if (rb) {
+      a.out = rb->dst;
+      a.rb_log = rb->log_rows;
+      a.rb_chunks = rb->chunks;
+      a.rb_col_stride = rb->col_stride;
+      a.rb_chunk_words = rb->chunk_words;
+      a.rb_halo = rb->halo;
+    }
     launch_strided<false>(p, a, (unsigned)((n << r) >> (p.K1 + p.logtc)), ncols, s);
+    return rb != nullptr;
   }
+  return false;
 }
 
 static inline void lde_columns(TableSet& ts, const u64* in, size_t in_stride, u64* out, size_t out_stride, u64* scratch,
                                int ncols, int L, int r, int mode, pbStream s) {
   transform_columns(ts, in, in_stride, out, out_stride, scratch, ncols, L, r, mode, s);
+}
+// LDE whose last pass writes row blocks (see StridedArgs::rb_*); false: `out` holds the plain LDE, nothing was written
+// to rb->dst.
+static inline bool lde_columns_row_blocks(TableSet& ts, const u64* in, size_t in_stride, u64* out, size_t out_stride,
+                                          u64* scratch, int ncols, int L, int r, int mode, const RowBlocks& rb, pbStream s) {
+  return transform_columns(ts, in, in_stride, out, out_stride, scratch, ncols, L, r, mode, s, &rb);
 }
 
 // coset iNTT (shift 7) of `ncols` columns of length n = 2^L: natural-order values on 7*<w> ->

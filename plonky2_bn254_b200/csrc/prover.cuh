@@ -220,25 +220,33 @@ static inline void prove_device(pb254_ctx* c, int kind, const u64* d_trace, size
     u64* rows = ar.alloc_n<u64>(Cpad * stride);
     const size_t mark = ar.off;
     u64* col_lde = ar.alloc_n<u64>(cper * N);
+    u64* send = ar.alloc_n<u64>(P * cper * stride);
     const std::string t = tag;
+    // Chunk q of the exchange: rows [q Nloc, (q + 1) Nloc + halo) (mod N) of this rank's columns, so that the
+    // receiver's buffer IS its row block with the next-row halo: [source rank][column][Nloc + halo] = [Cpad][stride].
+    // The last NTT pass writes this layout itself (ntt::RowBlocks); only transforms too small for a strided last pass
+    // are repacked by copies.
+    bool packed = false;
     {
       Stage st(c, ("lde " + t).c_str());
-      if (nc) ntt::lde_columns(c->tables, shard, n, col_lde, N, scratch_, (int)nc, L, r, ntt::FROM_VALUES_LDE, s);
+      int log_nloc = 0;
+      while (((size_t)1 << log_nloc) < Nloc) log_nloc++;
+      const ntt::RowBlocks rb = {send, log_nloc, (unsigned)P, stride, cper * stride, halo};
+      if (nc)
+        packed = ntt::lde_columns_row_blocks(c->tables, shard, n, col_lde, N, scratch_, (int)nc, L, r, ntt::FROM_VALUES_LDE, rb, s);
     }
     {
-      // Chunk q of the exchange: rows [q Nloc, (q + 1) Nloc + halo) (mod N) of this rank's columns, so that the
-      // receiver's buffer IS its row block with the next-row halo: [source rank][column][Nloc + halo] = [Cpad][stride].
       Stage st(c, ("exchange " + t).c_str());
-      u64* send = ar.alloc_n<u64>(P * cper * stride);
-      for (size_t q = 0; q < P; q++) {
-        u64* dst = send + q * cper * stride;
-        if (q + 1 < P) {
-          pb_copy2d(dst, stride * 8, col_lde + q * Nloc, N * 8, stride * 8, cper, s);
-        } else {  // the halo of the last block wraps around to row 0
-          pb_copy2d(dst, stride * 8, col_lde + q * Nloc, N * 8, Nloc * 8, cper, s);
-          pb_copy2d(dst + Nloc, stride * 8, col_lde, N * 8, halo * 8, cper, s);
+      if (nc && !packed)
+        for (size_t q = 0; q < P; q++) {
+          u64* dst = send + q * cper * stride;
+          if (q + 1 < P) {
+            pb_copy2d(dst, stride * 8, col_lde + q * Nloc, N * 8, stride * 8, cper, s);
+          } else {  // the halo of the last block wraps around to row 0
+            pb_copy2d(dst, stride * 8, col_lde + q * Nloc, N * 8, Nloc * 8, cper, s);
+            pb_copy2d(dst + Nloc, stride * 8, col_lde, N * 8, halo * 8, cper, s);
+          }
         }
-      }
       coll(comm->all_to_all(comm->user, send, rows, cper * stride * 8), "all_to_all");
     }
     {
