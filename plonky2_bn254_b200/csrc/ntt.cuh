@@ -369,7 +369,8 @@ struct RowBlocks {
 
 // INV: pass A (DIF, inverse roots; last round multiplies by tw4 and stores to `out`, any representatives).
 // !INV: pass D (DIT; first round multiplies by tw4, last round stores canonical values to `out`).
-template <int LOGTC, bool INV>
+// RB: pass D writes row blocks (StridedArgs::rb_*); a template parameter so that the plain kernel is unchanged.
+template <int LOGTC, bool INV, bool RB = false>
 PB_D void strided_body(u64* sm, unsigned bx, unsigned by, int nt, const StridedArgs& a) {
   constexpr int TC = 1 << LOGTC;
   const int R = 1 << a.K1;
@@ -417,7 +418,7 @@ PB_D void strided_body(u64* sm, unsigned bx, unsigned by, int nt, const StridedA
         } else {
           auto st_out = [&](int slot, u64 v) {
             const u64 cv = canon(v);
-            if (a.rb_log) {
+            if constexpr (RB) {
               const size_t row = ((size_t)slot << lrs) + (size_t)bx * TC + c;
               const size_t q = row >> a.rb_log, off = row & (((size_t)1 << a.rb_log) - 1);
               u64* base = a.out + (size_t)by * a.rb_col_stride;
@@ -585,10 +586,10 @@ PB_D void fused_body(u64* sm, unsigned bx, unsigned by, int nt, const FusedArgs&
 #ifndef NTT_LB_CTAS
 #define NTT_LB_CTAS 2
 #endif
-template <int LOGTC, bool INV>
+template <int LOGTC, bool INV, bool RB = false>
 static __global__ void __launch_bounds__(256, NTT_LB_CTAS) k_ntt_strided(const __grid_constant__ StridedArgs a) {
   extern __shared__ __align__(16) u64 ntt_sm[];
-  strided_body<LOGTC, INV>(ntt_sm, blockIdx.x, blockIdx.y, (int)blockDim.x, a);
+  strided_body<LOGTC, INV, RB>(ntt_sm, blockIdx.x, blockIdx.y, (int)blockDim.x, a);
 }
 static __global__ void __launch_bounds__(256, NTT_LB_CTAS) k_ntt_fused(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(16) u64 ntt_sm[];
@@ -609,6 +610,8 @@ static inline void set_smem_attrs() {
   PB_CUDA(cudaFuncSetAttribute(k_ntt_strided<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   PB_CUDA(cudaFuncSetAttribute(k_ntt_strided<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   PB_CUDA(cudaFuncSetAttribute(k_ntt_strided<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  PB_CUDA(cudaFuncSetAttribute(k_ntt_strided<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  PB_CUDA(cudaFuncSetAttribute(k_ntt_strided<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   PB_CUDA(cudaFuncSetAttribute(k_ntt_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   g_ntt_attr_set[dev] = true;
 }
@@ -616,7 +619,7 @@ static inline void set_smem_attrs() {
 
 static inline unsigned threads_for(size_t items) { return items >= 256 ? 256u : items >= 32 ? (unsigned)items : 32u; }
 
-template <bool INV>
+template <bool INV, bool RB = false>
 static inline void launch_strided(const Plan& p, const StridedArgs& a, unsigned tiles, int ncols, pbStream s) {
   const size_t smem = (((size_t)1 << (p.K1 + p.logtc)) + a.R.words + 4) * 8;
   const unsigned nt = threads_for(((size_t)1 << (p.K1 + p.logtc)) >> 4);
@@ -629,23 +632,23 @@ static inline void launch_strided(const Plan& p, const StridedArgs& a, unsigned 
     for (int by = 0; by < ncols; by++)
       for (unsigned bx = 0; bx < tiles; bx++) {
         if (p.logtc == 4)
-          strided_body<4, INV>(sm.data(), bx, (unsigned)by, (int)nt, a);
+          strided_body<4, INV, RB>(sm.data(), bx, (unsigned)by, (int)nt, a);
         else if (p.logtc == 3)
-          strided_body<3, INV>(sm.data(), bx, (unsigned)by, (int)nt, a);
+          strided_body<3, INV, RB>(sm.data(), bx, (unsigned)by, (int)nt, a);
         else if (p.logtc == 2)
-          strided_body<2, INV>(sm.data(), bx, (unsigned)by, (int)nt, a);
+          strided_body<2, INV, RB>(sm.data(), bx, (unsigned)by, (int)nt, a);
         else if (p.logtc == 1)
-          strided_body<1, INV>(sm.data(), bx, (unsigned)by, (int)nt, a);
+          strided_body<1, INV, RB>(sm.data(), bx, (unsigned)by, (int)nt, a);
         else
-          strided_body<0, INV>(sm.data(), bx, (unsigned)by, (int)nt, a);
+          strided_body<0, INV, RB>(sm.data(), bx, (unsigned)by, (int)nt, a);
       }
   }
 #else
   dim3 grid(tiles, (unsigned)ncols);
   if (p.logtc == 4)
-    k_ntt_strided<4, INV><<<grid, nt, smem, s>>>(a);
+    k_ntt_strided<4, INV, RB><<<grid, nt, smem, s>>>(a);
   else if (p.logtc == 3)
-    k_ntt_strided<3, INV><<<grid, nt, smem, s>>>(a);
+    k_ntt_strided<3, INV, RB><<<grid, nt, smem, s>>>(a);
   else
     throw Pb254Error(6, "ntt: size not supported");
   g_pb_launches++;
@@ -718,9 +721,11 @@ static inline bool transform_columns(TableSet& ts, const u64* in, size_t in_stri
       a.rb_col_stride = rb->col_stride;
       a.rb_chunk_words = rb->chunk_words;
       a.rb_halo = rb->halo;
+      launch_strided<false, true>(p, a, (unsigned)((n << r) >> (p.K1 + p.logtc)), ncols, s);
+      return true;
     }
     launch_strided<false>(p, a, (unsigned)((n << r) >> (p.K1 + p.logtc)), ncols, s);
-    return rb != nullptr;
+    return false;
   }
   return false;
 }
