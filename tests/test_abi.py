@@ -60,3 +60,24 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "oracle/" not in text.replace("the oracle", ""), f
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors of the header's structs (ffi.Config, ffi.Comm, ffi.ProofLayout) have the C compiler's sizes
+    and field offsets: a tiny C program including include/pb254.h prints them."""
+    import subprocess
+    from plonky2_bn254_b200 import ffi
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pb254.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %zu\\n", sizeof(pb254_config), offsetof(pb254_config, num_query_rounds),'
+                   ' offsetof(pb254_config, final_poly_bits), sizeof(pb254_proof_layout));\n'
+                   '  printf("%zu %zu %zu %zu %zu\\n", sizeof(pb254_comm), offsetof(pb254_comm, world), offsetof(pb254_comm, user),'
+                   ' offsetof(pb254_comm, all_to_all), offsetof(pb254_comm, all_gather));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    cfg, comm = ffi.Config, ffi.Comm
+    assert [int(x) for x in out[:4]] == [ctypes.sizeof(cfg), cfg.num_query_rounds.offset, cfg.final_poly_bits.offset,
+                                         ctypes.sizeof(ffi.ProofLayout)]
+    assert [int(x) for x in out[4:]] == [ctypes.sizeof(comm), comm.world.offset, comm.user.offset,
+                                         comm.all_to_all.offset, comm.all_gather.offset]
